@@ -1,0 +1,158 @@
+/*
+ * msq_b200.h -- C ABI of libmsq_b200.so: the sm_100a (B200) implementation of
+ * MaxSquareLoss's per-pixel adaptation-loss and evaluation hot path.
+ *
+ * The reference (shiyutang/MaxSquareLoss) is pure Python; it has no FFI.  The
+ * boundary it offers is class substitution at its factory sites
+ * (tools/solve_gta5.py:156-160, tools/solve_crosscity.py:99-102,
+ * tools/train_source.py:125).  Each entry point below is what a binding for
+ * that class/method would call; the reference interface it replaces is cited.
+ * The ctypes binding is maxsquareloss_b200/_lib.py; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C symbols, no exceptions, no ownership: the caller allocates every
+ *     device buffer (torch tensors in the Python shim) and passes raw device
+ *     pointers, sizes and the CUDA stream to enqueue on (cudaStream_t as void*).
+ *   - every call is asynchronous on `stream` and never synchronises the host.
+ *   - return value: 0 on success, a cudaError_t (>0) from a launch / memset, or
+ *     an MSQ_E_* code (<0) for argument errors.  msq_error_string() names it.
+ *   - tensors are dense row-major ("NCHW contiguous"), fp32; labels int64.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef MSQ_B200_H_
+#define MSQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSQ_ABI_VERSION 1
+#define MSQ_MAX_CLASSES 32          /* reference uses 13 / 16 / 19 */
+
+#define MSQ_E_BADARG   (-1)         /* null pointer, non-positive size, C > MSQ_MAX_CLASSES */
+#define MSQ_E_GEOMETRY (-2)         /* fused path needs H >= h and W >= w (the model only upsamples) */
+#define MSQ_E_SMEM     (-3)         /* tile does not fit shared memory */
+#define MSQ_E_ALIGN    (-4)         /* pointer not aligned for its element type */
+
+#define MSQ_MODE_MAXSQUARE 0        /* utils/loss.py:104-119  MaxSquareloss      */
+#define MSQ_MODE_IW        1        /* utils/loss.py:69-102   IW_MaxSquareloss   */
+
+typedef void* msq_stream_t;         /* cudaStream_t */
+
+int         msq_abi_version(void);
+const char* msq_error_string(int code);
+
+/* ---------------------------------------------------------------------------
+ * Loss buffers.  A forward call uses two device buffers (byte offsets from
+ * msq_state_layout_get):
+ *
+ * ACCUMULATORS (`accum`, accum_bytes): must be ZERO when a *_fwd call starts and
+ * are zero again when that call's kernels have finished (the last CTA to finish
+ * finalises and re-zeroes them), so ONE zero-initialised buffer per stream can
+ * be reused forever without a memset.  Not shareable between streams.
+ *   sumsq  uint64[N*C]  sum over pixels of q = sum_c p_c^2 in 2^-32 fixed point,
+ *                       bucketed by the pixel's argmax class (IW) or in bucket 0
+ *                       of each image (MaxSquare).  Integer, hence
+ *                       order-independent: the loss is bit-reproducible.
+ *   kept   uint64       number of prob elements != ignore_index (MaxSquare mean)
+ *   hist   uint32[N*C]  per-image class histogram being accumulated
+ *   flags  uint32       bit0: a non-finite value was seen (loss becomes NaN)
+ *   ticket uint32       CTA completion counter
+ *
+ * OUTPUTS (`out`, out_bytes): written by the forward, read by the backward.
+ *   sum_out   float64[N]   per-image sum of q (diagnostics / multi-GPU reduction)
+ *   kept_out  uint64       elements kept by the MaxSquare mask (local)
+ *   loss      float32      the scalar the reference's forward() returns
+ *   weights   float32[N*C] image-wise class weights (utils/loss.py:95); 1 for MaxSquare
+ *   hist_out  int32[N*C]   final per-image histogram (what utils/loss.py:92-94 computes)
+ *   stats     float64[1+C] [loss, sum over images of hist_out]: the rank-local
+ *                          partials, packed so that ONE NCCL all-reduce(sum) of
+ *                          this vector yields the global loss and class histogram
+ *                          when images are sharded over ranks (counts < 2^53 are
+ *                          exact in fp64)
+ * ------------------------------------------------------------------------- */
+typedef struct msq_state_layout {
+    int64_t sumsq_off, kept_off, hist_off, flags_off, ticket_off;   /* into accum */
+    int64_t accum_bytes;
+    int64_t sum_out_off, kept_out_off, loss_off, weights_off, hist_out_off, stats_off;   /* into out */
+    int64_t out_bytes;
+} msq_state_layout;
+
+int msq_state_layout_get(int n_images, int num_class, msq_state_layout* out);
+
+/* ---------------------------------------------------------------------------
+ * Strict drop-in: full-resolution probabilities in, as the reference's
+ * forward(pred, prob[, label]) receives them (`pred` is unused by the
+ * reference, utils/loss.py:84,117, and is not passed).
+ *
+ *   mode          MSQ_MODE_MAXSQUARE | MSQ_MODE_IW
+ *   prob          float32 [N,C,H*W]
+ *   label         int64 [N,H*W] or NULL  (IW only, utils/loss.py:87-88: the map
+ *                 whose values are counted; weights are still gathered by argmax)
+ *   ratio         IW ratio (utils/loss.py:74), ignored for MaxSquare
+ *   ignore_index  utils/loss.py:72,107 (compared against prob as float)
+ *   n_images_norm normaliser N of utils/loss.py:100 (pass the GLOBAL batch size
+ *                 when images are sharded over ranks; 0 means N)
+ *   accum, out    device buffers, see above
+ * ------------------------------------------------------------------------- */
+int msq_prob_fwd(int mode, const float* prob, int n, int num_class, int64_t hw,
+                 const int64_t* label, double ratio, int ignore_index, int n_images_norm,
+                 void* accum, void* out, msq_stream_t stream);
+
+/* dL/dprob = grad_out * d(loss)/d(prob), written densely (zeros where masked).
+ *   grad_out   device pointer to the 0-dim fp32 upstream gradient (callers
+ *              scale the loss by lambda_target before backward,
+ *              tools/solve_gta5.py:199,217)
+ *   out        the output buffer msq_prob_fwd filled (weights / kept_out are read)   */
+int msq_prob_bwd(int mode, const float* prob, int n, int num_class, int64_t hw,
+                 int ignore_index, int n_images_norm, const void* out,
+                 const float* grad_out, float* grad_prob, msq_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused: low-resolution head logits in.  Absorbs the model's
+ * F.interpolate(..., mode='bilinear', align_corners=True)
+ * (graphs/models/deeplab_multi.py:124,128), the trainer's F.softmax(pred, 1)
+ * (tools/solve_gta5.py:182-183) and the loss; the backward goes through the
+ * softmax and the bilinear adjoint and writes dL/dlogits at h x w.  No
+ * full-resolution tensor is read or written.
+ *   logits      float32 [N,C,h,w]
+ *   label       int64 [N,H,W] or NULL (IW `label=` argument, full resolution)
+ *   grad_logits float32 [N,C,h,w], overwritten
+ * ------------------------------------------------------------------------- */
+int msq_fused_fwd(int mode, const float* logits, int n, int num_class, int h, int w,
+                  int out_h, int out_w, const int64_t* label, double ratio,
+                  int n_images_norm, void* accum, void* out, msq_stream_t stream);
+
+int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, int w,
+                  int out_h, int out_w, int n_images_norm, const void* out,
+                  const float* grad_out, float* grad_logits, msq_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Evaluation: Eval.__generate_matrix / add_batch (utils/eval.py:109-121).
+ *   cm      uint64 [C*C], row = ground truth, column = prediction, ACCUMULATED
+ *   errs    uint32 [2], OR-ed: [0] a flattened index C*gt+pred was negative
+ *           (numpy.bincount raises ValueError), [1] it was >= C*C (the
+ *           reference's reshape raises ValueError).  May be NULL for the
+ *           logits variant (argmax is always in range).
+ * gt values outside [0,C) are ignored (utils/eval.py:111).
+ * ------------------------------------------------------------------------- */
+int msq_confusion_i64(const int64_t* gt, const int64_t* pred, int64_t npix, int num_class,
+                      unsigned long long* cm, unsigned int* errs, msq_stream_t stream);
+
+/* Same with the callers' np.argmax(pred, axis=1) (tools/train_source.py:282,459)
+ * fused in: logits float32 [N,C,H*W], first maximum wins, NaN counts as maximum. */
+int msq_confusion_logits_f32(const int64_t* gt, const float* logits, int n, int num_class,
+                             int64_t hw, unsigned long long* cm, msq_stream_t stream);
+
+/* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "fused_rows" R; 0 =
+ * automatic).  Results never depend on them. */
+int msq_tune_set(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSQ_B200_H_ */

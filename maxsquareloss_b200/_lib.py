@@ -1,0 +1,93 @@
+"""ctypes binding of libmsq_b200.so (C ABI in include/msq_b200.h).
+
+There is no CPU fallback: if the library is missing this module raises, and every
+entry point refuses non-CUDA tensors.
+"""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libmsq_b200.so")
+
+MAX_CLASSES = 32
+MODE_MAXSQUARE = 0
+MODE_IW = 1
+
+#: every symbol include/msq_b200.h declares
+SYMBOLS = ("msq_abi_version", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
+           "msq_fused_fwd", "msq_fused_bwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set")
+
+
+class StateLayout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in (
+        "sumsq_off", "kept_off", "hist_off", "flags_off", "ticket_off", "accum_bytes",
+        "sum_out_off", "kept_out_off", "loss_off", "weights_off", "hist_out_off", "stats_off", "out_bytes")]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared library once.  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m maxsquareloss_b200.build` "
+                "(nvcc, sm_100a).  maxsquareloss_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        c = ctypes
+        vp, i32, i64, dbl = c.c_void_p, c.c_int, c.c_int64, c.c_double
+        lib.msq_abi_version.restype = i32
+        lib.msq_abi_version.argtypes = []
+        lib.msq_error_string.restype = c.c_char_p
+        lib.msq_error_string.argtypes = [i32]
+        lib.msq_state_layout_get.restype = i32
+        lib.msq_state_layout_get.argtypes = [i32, i32, c.POINTER(StateLayout)]
+        lib.msq_prob_fwd.restype = i32
+        lib.msq_prob_fwd.argtypes = [i32, vp, i32, i32, i64, vp, dbl, i32, i32, vp, vp, vp]
+        lib.msq_prob_bwd.restype = i32
+        lib.msq_prob_bwd.argtypes = [i32, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp]
+        lib.msq_fused_fwd.restype = i32
+        lib.msq_fused_fwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, vp, dbl, i32, vp, vp, vp]
+        lib.msq_fused_bwd.restype = i32
+        lib.msq_fused_bwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.msq_confusion_i64.restype = i32
+        lib.msq_confusion_i64.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+        lib.msq_confusion_logits_f32.restype = i32
+        lib.msq_confusion_logits_f32.argtypes = [vp, vp, i32, i32, i64, vp, vp]
+        lib.msq_tune_set.restype = i32
+        lib.msq_tune_set.argtypes = [c.c_char_p, i32]
+        if lib.msq_abi_version() != 1:
+            raise RuntimeError("libmsq_b200.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().msq_error_string(code).decode()
+        raise RuntimeError(f"libmsq_b200: {msg} (code {code})")
+
+
+_layouts = {}
+
+
+def state_layout(n, c):
+    key = (n, c)
+    lay = _layouts.get(key)
+    if lay is None:
+        lay = StateLayout()
+        check(load().msq_state_layout_get(n, c, ctypes.byref(lay)))
+        _layouts[key] = lay
+    return lay
+
+
+def tune(key, value):
+    check(load().msq_tune_set(key.encode(), int(value)))

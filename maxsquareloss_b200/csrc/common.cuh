@@ -1,0 +1,223 @@
+// Shared device helpers for libmsq_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/msq_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmsq_b200 targets sm_100a (B200) only"
+#endif
+
+namespace msq {
+
+constexpr int kSMs = 148;                       // B200: 2 dies x 74 SMs
+constexpr float kFix = 4294967296.0f;           // 2^32: fixed-point scale of q = sum_c p_c^2
+constexpr double kInvFix = 1.0 / 4294967296.0;
+constexpr unsigned kFlagNonFinite = 1u;
+
+// Carved view of the caller's state buffer (see msq_state_layout in the header).
+struct State {
+    unsigned int* hist;
+    unsigned long long* sumsq;
+    unsigned long long* kept;
+    unsigned int* flags;
+    unsigned int* ticket;
+    float* loss;
+    float* weights;
+    int* hist_out;
+    double* sum_out;
+    unsigned long long* kept_out;
+    double* stats;
+};
+
+__host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+inline msq_state_layout make_layout(int n, int c) {
+    msq_state_layout L;
+    int64_t nc = (int64_t)n * c, off = 0;
+    L.sumsq_off = off;  off += nc * 8;                 // 8-byte members first
+    L.kept_off = off;   off += 8;
+    L.hist_off = off;   off += nc * 4;
+    L.flags_off = off;  off += 4;
+    L.ticket_off = off; off += 4;
+    L.accum_bytes = align_up(off, 16);
+    off = 0;
+    L.sum_out_off = off;  off += (int64_t)n * 8;
+    L.kept_out_off = off; off += 8;
+    L.loss_off = off;     off += 4;
+    off = align_up(off, 16);
+    L.weights_off = off;  off += nc * 4;
+    L.hist_out_off = off; off += nc * 4;
+    off = align_up(off, 16);
+    L.stats_off = off;    off += (int64_t)(1 + c) * 8;
+    L.out_bytes = align_up(off, 16);
+    return L;
+}
+
+inline State carve(void* accum, void* out, int n, int c) {
+    msq_state_layout L = make_layout(n, c);
+    char* a = (char*)accum;
+    char* o = (char*)out;
+    State s;
+    s.hist = (unsigned int*)(a + L.hist_off);
+    s.sumsq = (unsigned long long*)(a + L.sumsq_off);
+    s.kept = (unsigned long long*)(a + L.kept_off);
+    s.flags = (unsigned int*)(a + L.flags_off);
+    s.ticket = (unsigned int*)(a + L.ticket_off);
+    s.loss = (float*)(o + L.loss_off);
+    s.weights = (float*)(o + L.weights_off);
+    s.hist_out = (int*)(o + L.hist_out_off);
+    s.sum_out = (double*)(o + L.sum_out_off);
+    s.kept_out = (unsigned long long*)(o + L.kept_out_off);
+    s.stats = (double*)(o + L.stats_off);
+    return s;
+}
+
+// ---- streaming 128-bit loads/stores: read-once data must not pollute L1 -------------
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ longlong2 ldg_stream_l2(const int64_t* p) {
+    longlong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ long long ldg_stream_l1(const int64_t* p) {
+    long long r;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// q (or a short run-sum of q's) -> 2^-32 fixed point.  Exact for finite q >= 2^-8:
+// scaling by 2^32 is exact and the float then holds an integer < 2^64.
+__device__ __forceinline__ unsigned long long to_fix(float qsum) {
+    return __float2ull_rn(qsum * kFix);
+}
+
+// Image-wise class weight, utils/loss.py:95, with the reference's fp32 roundings:
+//   1 / max( fl(hist^r) * fl(total^(1-r)), 1 )     (r and 1-r cast to fp32, as
+//   torch.pow(float32 tensor, python scalar) does).  pow itself is evaluated in
+//   fp64 and rounded once, i.e. it is a <=0.5 ulp fp32 pow.
+__device__ __forceinline__ float iw_weight(float hist, float total, float r32, float omr32) {
+    float a = (float)pow((double)hist, (double)r32);
+    float b = (float)pow((double)total, (double)omr32);
+    float m = fmaxf(__fmul_rn(a, b), 1.0f);
+    return __fdiv_rn(1.0f, m);
+}
+
+
+// ---------------------------------------------------------------------------------
+// Finalisation, run by every thread of the LAST CTA to finish (ticket pattern):
+// turns the integer accumulators into the reference's scalar, the per-image
+// weights and the final histogram, then re-zeroes the accumulators so the state
+// buffer is ready for the next call without a memset.
+//   IW        (utils/loss.py:95,100):  loss = -(1/(Nn*C)) sum_n sum_k w_nk * S_nk
+//   MaxSquare (utils/loss.py:118):     loss = -(sum q) / (2 * kept)
+// Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool take_ticket_is_last(unsigned int* ticket, unsigned total_ctas) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == total_ctas - 1);
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+__device__ inline void finalize_loss(const State& st, int mode, int n, int C, float r32, float omr32,
+                                     int n_norm, unsigned long long kept_dense) {
+    __shared__ double s_red[32];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int nc = n * C;
+    volatile unsigned int* vhist = st.hist;
+    volatile unsigned long long* vsum = st.sumsq;
+    double part = 0.0;
+    for (int idx = tid; idx < nc; idx += nthr) {
+        const int img = idx / C;
+        const unsigned hcnt = vhist[idx];
+        const double S = (double)vsum[idx] * kInvFix;
+        float wgt = 1.0f;
+        if (mode == MSQ_MODE_IW) {
+            unsigned total = 0;
+            for (int k = 0; k < C; ++k) total += vhist[img * C + k];
+            wgt = iw_weight((float)hcnt, (float)total, r32, omr32);
+            part += (double)wgt * S;
+        } else {
+            part += S;
+        }
+        st.weights[idx] = wgt;
+        st.hist_out[idx] = (int)hcnt;
+    }
+    for (int img = tid; img < n; img += nthr) {
+        double s = 0.0;
+        for (int k = 0; k < C; ++k) s += (double)vsum[img * C + k] * kInvFix;
+        st.sum_out[img] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < (nthr + 31) / 32; ++i) tot += s_red[i];
+        const unsigned long long kept_local = (kept_dense != 0ull) ? kept_dense : *((volatile unsigned long long*)st.kept);
+        const double scale = (double)n_norm / (double)n;
+        double loss;
+        if (mode == MSQ_MODE_IW) loss = -tot / ((double)n_norm * (double)C);
+        else loss = -tot / (2.0 * (double)kept_local * scale);
+        if (*((volatile unsigned int*)st.flags) & kFlagNonFinite) loss = __longlong_as_double(0x7ff8000000000000LL);
+        *st.loss = (float)loss;
+        *st.kept_out = kept_local;
+        st.stats[0] = loss;
+    }
+    for (int k = tid; k < C; k += nthr) {
+        unsigned long long tot = 0ull;
+        for (int img = 0; img < n; ++img) tot += vhist[img * C + k];
+        st.stats[1 + k] = (double)tot;
+    }
+    __syncthreads();
+    // self-clean the accumulators (stream order makes this visible to the next call)
+    for (int idx = tid; idx < nc; idx += nthr) { st.hist[idx] = 0u; st.sumsq[idx] = 0ull; }
+    if (tid == 0) { *st.kept = 0ull; *st.flags = 0u; *st.ticket = 0u; }
+}
+
+}  // namespace msq
+
+#define MSQ_CHECK_LAUNCH()                       \
+    do {                                         \
+        cudaError_t e__ = cudaGetLastError();    \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)

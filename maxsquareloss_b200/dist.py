@@ -1,0 +1,63 @@
+"""Sharding by image across the GPUs of one box, and the one small all-reduce per step.
+
+The reference is single-GPU (``nn.DataParallel(model, device_ids=[0])``,
+``tools/train_source.py:133-136``); nothing here replaces reference code.  The
+path shards naturally: image-wise weights are per image (``utils/loss.py:91-97``),
+MaxSquare is a plain sum, confusion counts are additive (``utils/eval.py:121``).
+Each rank runs the kernels on its own block of images with the loss normaliser
+set to the GLOBAL batch (``crit.global_batch``), and the only exchange is ONE
+all-reduce(sum) of a packed float64 vector
+
+    [ loss_partial | class_hist[C] | confusion[C*C] ]        (8*(1+C+C*C) bytes, ~3 KB)
+
+over NCCL/NVLink (gloo in the CPU tests).  Counts below 2**53 are exact in
+fp64, so the integers come back bit-exact.  The dL/dlogits of a rank's images
+depends on nothing from other ranks, so the gradient path has no collective.
+"""
+import torch
+import torch.distributed as dist
+
+
+def image_shard(n_total, rank, world):
+    """Contiguous block [lo, hi) of the global batch owned by ``rank`` (cfg 3:
+    8 images over 2/4/8 ranks).  Remainder images go to the lowest ranks."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def stats_len(num_class, with_confusion=True):
+    return 1 + num_class + (num_class * num_class if with_confusion else 0)
+
+
+def pack_stats(loss_partial, class_hist, confusion=None, out=None):
+    """-> float64 vector [loss, hist(C), cm(C*C)?] on the inputs' device."""
+    c = class_hist.numel()
+    n = stats_len(c, confusion is not None)
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=class_hist.device)
+    out[0] = loss_partial
+    out[1:1 + c] = class_hist.reshape(-1)
+    if confusion is not None:
+        out[1 + c:] = confusion.reshape(-1)
+    return out
+
+
+def unpack_stats(buf, num_class):
+    """-> (loss float64 0-dim, hist int64 (C,), cm int64 (C,C) or None)."""
+    c = num_class
+    loss = buf[0]
+    hist = buf[1:1 + c].round().to(torch.int64)
+    cm = None
+    if buf.numel() >= 1 + c + c * c:
+        cm = buf[1 + c:1 + c + c * c].round().to(torch.int64).view(c, c)
+    return loss, hist, cm
+
+
+def allreduce_stats(buf, group=None, async_op=False):
+    """Sum ``buf`` over the ranks (no-op without an initialised process group).
+    With ``async_op`` the NCCL work handle is returned so that the collective
+    overlaps the backward kernel; call ``.wait()`` before reading ``buf``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=async_op)

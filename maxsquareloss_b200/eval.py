@@ -1,0 +1,221 @@
+"""Host side of the evaluation accumulator: the reference's ``Eval`` API
+(``utils/eval.py:14-124``) over the sm_100a confusion-matrix kernels.
+
+``add_batch`` accepts what the reference's callers pass (numpy ``gt``/``pred``
+maps, ``tools/train_source.py:280-283,455-459``) and, as the fast path, CUDA
+tensors -- including the raw logits ``(N,C,H,W)``, in which case the callers'
+``np.argmax(pred, axis=1)`` is fused into the kernel and the 40 MB/image D2H of
+the logits disappears.  Counts are accumulated on the device as uint64 and
+folded into the float64 ``confusion_matrix`` attribute when it (or any metric)
+is read; the metrics themselves are the reference's NumPy expressions on that
+float64 matrix, so they are bit-identical.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+
+#: class names the reference prints (datasets/cityscapes_Dataset.py:379-400)
+name_classes = ['road', 'sidewalk', 'building', 'wall', 'fence', 'pole', 'trafflight', 'traffsign',
+                'vegetation', 'terrain', 'sky', 'person', 'rider', 'car', 'truck', 'bus', 'train',
+                'motorcycle', 'bicycle', 'unlabeled']
+
+synthia_set_16 = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 15, 17, 18]     # utils/eval.py:10
+synthia_set_13 = [0, 1, 2, 6, 7, 8, 10, 11, 12, 13, 15, 17, 18]              # utils/eval.py:11
+synthia_set_16_to_13 = [0, 1, 2, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]         # utils/eval.py:12
+
+
+def _to_device_labels(a, device, num_class, is_gt):
+    """numpy / tensor label map -> contiguous int64 CUDA tensor with the reference's
+    conversions: float ground truth is range-checked as float, then truncated
+    (``gt_image[mask].astype('int')``, utils/eval.py:111-112)."""
+    t = torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a
+    if t.device != device:
+        if t.device.type == "cpu" and t.numel() > 0:
+            t = t.contiguous()
+            try:
+                t = t.pin_memory()
+            except RuntimeError:
+                pass
+        t = t.to(device, non_blocking=True)
+    if t.is_floating_point():
+        if is_gt:
+            ok = (t >= 0) & (t < num_class)
+            t = torch.where(ok, t.trunc().to(torch.int64), torch.full((), -1, dtype=torch.int64, device=device))
+        else:
+            t = t.to(torch.int64)
+    elif t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+class Eval:
+    def __init__(self, num_class, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("maxsquareloss_b200.Eval needs a CUDA device: there is no CPU fallback")
+        if num_class < 1 or num_class > _lib.MAX_CLASSES:
+            raise RuntimeError(f"num_class must be in [1, {_lib.MAX_CLASSES}]")
+        _lib.load()
+        self.num_class = num_class
+        self.ignore_index = None
+        self.synthia = True if num_class == 16 else False
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._host = np.zeros((num_class,) * 2)
+        # [C*C counts | 2 error flags (as one int64: two uint32)]
+        self._dev = torch.zeros(num_class * num_class + 1, dtype=torch.int64, device=self.device)
+        self._pending = False
+
+    # ------------------------------------------------------------------ accumulate
+    def add_batch(self, gt_image, pre_image):
+        """``gt_image``: (N,H,W) labels, -1 / >= C ignored.  ``pre_image``: (N,H,W) class
+        ids, or floating CUDA logits (N,C,H,W) to have the argmax taken on the device."""
+        if isinstance(pre_image, torch.Tensor) and pre_image.is_floating_point() and \
+                pre_image.dim() == np.ndim(gt_image) + 1:
+            return self.add_batch_logits(gt_image, pre_image)
+        # assert the size of two images are same (utils/eval.py:119)
+        assert tuple(gt_image.shape) == tuple(pre_image.shape)
+        host_call = not (isinstance(gt_image, torch.Tensor) and gt_image.is_cuda and
+                         isinstance(pre_image, torch.Tensor) and pre_image.is_cuda)
+        gt = _to_device_labels(gt_image, self.device, self.num_class, True)
+        pr = _to_device_labels(pre_image, self.device, self.num_class, False)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        cm_ptr = self._dev.data_ptr()
+        _lib.check(_lib.load().msq_confusion_i64(gt.data_ptr(), pr.data_ptr(), gt.numel(), self.num_class,
+                                                 cm_ptr, cm_ptr + 8 * self.num_class ** 2, stream))
+        self._pending = True
+        if host_call:
+            # numpy callers get the reference's synchronous behaviour, incl. ValueError now
+            self._fold()
+
+    def add_batch_logits(self, gt_image, logits):
+        """Fused ``np.argmax(logits, axis=1)`` + ``add_batch`` (tools/train_source.py:457-459,492)."""
+        if not (isinstance(logits, torch.Tensor) and logits.is_cuda and logits.dtype == torch.float32):
+            raise RuntimeError("logits must be a float32 CUDA tensor (N,C,H,W)")
+        n, c = logits.shape[0], logits.shape[1]
+        assert tuple(gt_image.shape) == (n,) + tuple(logits.shape[2:])
+        if c != self.num_class:
+            raise ValueError(f"logits have {c} classes, Eval was built with {self.num_class}")
+        gt = _to_device_labels(gt_image, self.device, self.num_class, True)
+        lg = logits.contiguous()
+        hw = lg.numel() // max(n * c, 1)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().msq_confusion_logits_f32(gt.data_ptr(), lg.data_ptr(), n, c, hw,
+                                                        self._dev.data_ptr(), stream))
+        self._pending = True
+
+    def _fold(self):
+        """device counts -> host float64 matrix (one small D2H, synchronises)."""
+        if not self._pending:
+            return
+        c2 = self.num_class ** 2
+        host = self._dev.cpu().numpy()
+        self._dev.zero_()
+        self._pending = False
+        flags = int(host[c2])
+        if flags & 0xFFFFFFFF:
+            raise ValueError("'list' argument must have no negative elements")      # numpy.bincount's message
+        if flags >> 32:
+            raise ValueError(f"cannot reshape array into shape ({self.num_class},{self.num_class})")
+        self._host += host[:c2].reshape(self.num_class, self.num_class)
+
+    @property
+    def confusion_matrix(self):
+        self._fold()
+        return self._host
+
+    @confusion_matrix.setter
+    def confusion_matrix(self, value):
+        self._dev.zero_()
+        self._pending = False
+        self._host = np.asarray(value, dtype=np.float64)
+
+    def device_counts(self):
+        """(C,C) int64 CUDA tensor of the counts not yet folded to the host (for an
+        NCCL all-reduce without a host round trip)."""
+        return self._dev[:self.num_class ** 2].view(self.num_class, self.num_class)
+
+    def reset(self):
+        self._dev.zero_()
+        self._pending = False
+        self._host = np.zeros((self.num_class,) * 2)
+
+    # ------------------------------------------------------------------ metrics (utils/eval.py:22-106)
+    def _pick(self, per_class, out_16_13):
+        if self.synthia:
+            return np.nanmean(per_class[:self.ignore_index]), np.nanmean(per_class[synthia_set_16_to_13])
+        if out_16_13:
+            return np.nanmean(per_class[synthia_set_16]), np.nanmean(per_class[synthia_set_13])
+        return np.nanmean(per_class[:self.ignore_index])
+
+    def _ratios(self):
+        cm = self.confusion_matrix
+        tp, rows, cols = np.diag(cm), cm.sum(axis=1), cm.sum(axis=0)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            return cm, tp, rows, cols, tp / rows, tp / (rows + cols - tp), tp / cols
+
+    def Pixel_Accuracy(self):
+        cm = self.confusion_matrix
+        if np.sum(cm) == 0:
+            print("Attention: pixel_total is zero!!!")
+            return 0
+        return np.diag(cm).sum() / cm.sum()
+
+    def Mean_Pixel_Accuracy(self, out_16_13=False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            return self._pick(self._ratios()[4], out_16_13)
+
+    def Mean_Intersection_over_Union(self, out_16_13=False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            return self._pick(self._ratios()[5], out_16_13)
+
+    def Mean_Precision(self, out_16_13=False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            return self._pick(self._ratios()[6], out_16_13)
+
+    def Frequency_Weighted_Intersection_over_Union(self, out_16_13=False):
+        cm, tp, rows, cols, _, _, _ = self._ratios()
+        with np.errstate(divide='ignore', invalid='ignore'):
+            fw = np.multiply(rows, tp) / (rows + cols - tp)
+        total = np.sum(cm)
+
+        def nansum_in_order(v):     # the reference sums the non-NaN entries left to right
+            s = 0
+            for x in v:
+                if not np.isnan(x):
+                    s = s + x
+            return s / total
+        with np.errstate(divide='ignore', invalid='ignore'):
+            if self.synthia:
+                return nansum_in_order(fw), nansum_in_order(fw[synthia_set_16_to_13])
+            if out_16_13:
+                return nansum_in_order(fw[synthia_set_16]), nansum_in_order(fw[synthia_set_13])
+            return nansum_in_order(fw)
+
+    def Print_Every_class_Eval(self, out_16_13=False):
+        cm, _, rows, cols, mpa, miou, prec = self._ratios()
+        with np.errstate(divide='ignore', invalid='ignore'):
+            class_ratio = rows / np.sum(cm)
+            pred_ratio = cols / np.sum(cm)
+        print('===>Everyclass:\t' + 'MPA\t' + 'MIoU\t' + 'PC\t' + 'Ratio\t' + 'Pred_Retio')
+        if out_16_13:
+            miou = miou[synthia_set_16]
+
+        def pct(v):
+            return str(round(v * 100, 2)) if not np.isnan(v) else 'nan'
+        for k in range(len(miou)):
+            print('===>' + name_classes[k] + ':\t' + pct(mpa[k]) + '\t' + pct(miou[k]) + '\t' + pct(prec[k]) +
+                  '\t' + pct(class_ratio[k]) + '\t' + pct(pred_ratio[k]))
+
+
+def fast_hist(gt, pred, num_class, device=None):
+    """(C,C) int64 confusion matrix of one (gt, pred) pair; rows = ground truth.
+    Public alias of the reference's private ``Eval._Eval__generate_matrix``
+    (``utils/eval.py:109-115``).  ``pred`` may be class ids or CUDA logits."""
+    ev = Eval(num_class, device=device)
+    ev.add_batch(gt, pred)
+    return ev.confusion_matrix.astype(np.int64)

@@ -1,0 +1,271 @@
+"""Host side of the adaptation losses: the reference's ``nn.Module`` API over the
+sm_100a kernels in ``csrc/`` (C ABI: ``include/msq_b200.h``).
+
+Drop-in for ``utils/loss.py`` of shiyutang/MaxSquareLoss:
+
+* ``MaxSquareloss(ignore_index=-1, num_class=19).forward(pred, prob)``
+  (``utils/loss.py:104-119``)
+* ``IW_MaxSquareloss(ignore_index=-1, num_class=19, ratio=0.2).forward(pred, prob, label=None)``
+  (``utils/loss.py:69-102``)
+
+Two entry modes:
+
+strict   ``forward(pred, prob[, label])`` exactly as the trainers call it
+         (``tools/solve_gta5.py:199``): ``prob`` is the full-resolution softmax
+         output, ``pred`` is ignored (the reference ignores it too), the gradient
+         is returned w.r.t. ``prob``.
+fused    ``forward(head_logits, out_size=(H, W)[, label=...])`` with ``prob`` omitted:
+         ``head_logits`` are the LOW-resolution classifier outputs (N,C,h,w); the
+         model's ``F.interpolate(..., 'bilinear', align_corners=True)``
+         (``graphs/models/deeplab_multi.py:124,128``) and the trainer's
+         ``F.softmax`` are done inside the kernels and the gradient is returned
+         w.r.t. the low-resolution logits.
+
+Differences from the reference, all deliberate:
+
+* the IW loss accepts N >= 2 (the reference raises, ``utils/loss.py:98-100`` lacks
+  an ``unsqueeze(1)``): per-image weights, i.e. the mean over images of the N=1 loss;
+* nothing synchronises the host (the reference does a D2H + CPU histc + H2D per image);
+* CUDA fp32 tensors only -- ``RuntimeError`` otherwise; there is no CPU fallback.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_accum_cache = {}
+
+
+def _accum_buffer(device, nbytes):
+    """Zero-initialised, self-cleaning accumulator buffer, one per (device, stream)."""
+    stream = torch.cuda.current_stream(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    buf = _accum_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=device)
+        _accum_cache[key] = buf
+    return buf, stream.cuda_stream
+
+
+def reset_workspaces():
+    """Drop the cached accumulator buffers (only needed after a CUDA error)."""
+    _accum_cache.clear()
+
+
+def _require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: maxsquareloss_b200 has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 4:
+        raise RuntimeError(f"{name} must be (N,C,H,W), got shape {tuple(t.shape)}")
+
+
+def _prep_label(label, device, shape, name):
+    if label is None:
+        return None
+    if not isinstance(label, torch.Tensor):
+        label = torch.as_tensor(label)
+    label = label.to(device=device, dtype=torch.int64, non_blocking=True)
+    if tuple(label.shape) != tuple(shape):
+        raise RuntimeError(f"{name} must have shape {tuple(shape)}, got {tuple(label.shape)}")
+    return label.contiguous()
+
+
+class _Outputs:
+    """Views into the per-call output buffer of a forward."""
+
+    def __init__(self, buf, n, c):
+        lay = _lib.state_layout(n, c)
+        self.buf = buf
+        self.loss = buf[lay.loss_off:lay.loss_off + 4].view(torch.float32).reshape(())
+        self.weights = buf[lay.weights_off:lay.weights_off + 4 * n * c].view(torch.float32).view(n, c)
+        self.hist = buf[lay.hist_out_off:lay.hist_out_off + 4 * n * c].view(torch.int32).view(n, c)
+        self.sum_q = buf[lay.sum_out_off:lay.sum_out_off + 8 * n].view(torch.float64)
+        self.stats = buf[lay.stats_off:lay.stats_off + 8 * (1 + c)].view(torch.float64)
+
+
+def _grad_out_ptr(grad_out, device):
+    g = grad_out
+    if g.device != device or g.dtype != torch.float32:
+        g = g.to(device=device, dtype=torch.float32)
+    return g.contiguous()
+
+
+class _ProbLoss(torch.autograd.Function):
+    """Strict drop-in: full-resolution probabilities (kernels K3/K4)."""
+
+    @staticmethod
+    def forward(ctx, prob, label, mode, num_class, ratio, ignore_index, n_norm, sink):
+        n, c, h, w = prob.shape
+        prob_c = prob.contiguous()
+        lay = _lib.state_layout(n, c)
+        accum, stream = _accum_buffer(prob.device, lay.accum_bytes)
+        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=prob.device)
+        _lib.check(_lib.load().msq_prob_fwd(
+            mode, prob_c.data_ptr(), n, c, h * w, label.data_ptr() if label is not None else None,
+            float(ratio), int(ignore_index), int(n_norm), accum.data_ptr(), out.data_ptr(), stream))
+        o = _Outputs(out, n, c)
+        sink.append(o)
+        ctx.save_for_backward(prob_c)
+        ctx.out = out
+        ctx.cfg = (mode, ignore_index, n_norm)
+        return o.loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 8
+        (prob,) = ctx.saved_tensors
+        mode, ignore_index, n_norm = ctx.cfg
+        n, c, h, w = prob.shape
+        go = _grad_out_ptr(grad_out, prob.device)
+        grad = torch.empty_like(prob)
+        stream = torch.cuda.current_stream(prob.device).cuda_stream
+        _lib.check(_lib.load().msq_prob_bwd(
+            mode, prob.data_ptr(), n, c, h * w, int(ignore_index), int(n_norm), ctx.out.data_ptr(),
+            go.data_ptr(), grad.data_ptr(), stream))
+        return (grad,) + (None,) * 7
+
+
+class _FusedLoss(torch.autograd.Function):
+    """Fused: low-resolution head logits (kernels K1/K2)."""
+
+    @staticmethod
+    def forward(ctx, logits, label, out_size, mode, num_class, ratio, n_norm, sink):
+        n, c, h, w = logits.shape
+        H, W = int(out_size[0]), int(out_size[1])
+        lo = logits.contiguous()
+        lay = _lib.state_layout(n, c)
+        accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
+        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
+        _lib.check(_lib.load().msq_fused_fwd(
+            mode, lo.data_ptr(), n, c, h, w, H, W, label.data_ptr() if label is not None else None,
+            float(ratio), int(n_norm), accum.data_ptr(), out.data_ptr(), stream))
+        o = _Outputs(out, n, c)
+        sink.append(o)
+        ctx.save_for_backward(lo)
+        ctx.out = out
+        ctx.cfg = (mode, H, W, n_norm)
+        return o.loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 8
+        (lo,) = ctx.saved_tensors
+        mode, H, W, n_norm = ctx.cfg
+        n, c, h, w = lo.shape
+        go = _grad_out_ptr(grad_out, lo.device)
+        grad = torch.empty_like(lo)
+        stream = torch.cuda.current_stream(lo.device).cuda_stream
+        _lib.check(_lib.load().msq_fused_bwd(
+            mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(), go.data_ptr(),
+            grad.data_ptr(), stream))
+        return (grad,) + (None,) * 7
+
+
+class _LossBase(nn.Module):
+    _mode = None
+
+    def __init__(self, ignore_index=-1, num_class=19):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.num_class = num_class
+        #: normaliser N of utils/loss.py:100 when the batch is sharded by image over
+        #: ranks: set to the GLOBAL batch size (0 = this call's own N)
+        self.global_batch = 0
+        #: device tensors of the most recent forward (no host sync to produce them)
+        self.last_hist = None        # (N,C) int32 per-image argmax/label histogram (IW)
+        self.last_weights = None     # (N,C) float32 image-wise class weights (IW)
+        self.last_sum_q = None       # (N,)  float64 per-image sum over pixels of sum_c p_c^2
+        self.last_stats = None       # (1+C,) float64 [loss, class histogram summed over images]: all-reduce me
+
+    def _check_classes(self, c):
+        if c != self.num_class:
+            raise ValueError(f"tensor has {c} classes but the loss was built with num_class={self.num_class}")
+        if c > _lib.MAX_CLASSES:
+            raise RuntimeError(f"num_class={c} exceeds the kernels' limit of {_lib.MAX_CLASSES}")
+
+    def _publish(self, sink):
+        o = sink[0]
+        self.last_hist, self.last_weights, self.last_sum_q, self.last_stats = o.hist, o.weights, o.sum_q, o.stats
+
+    def _run(self, pred, prob, label, out_size, ratio):
+        sink = []
+        if prob is None:
+            if out_size is None:
+                raise RuntimeError("fused mode needs out_size=(H, W): forward(head_logits, out_size=...)")
+            _require_cuda_f32(pred, "head logits")
+            self._check_classes(pred.shape[1])
+            # a softmax output never equals an ignore value outside [0,1], so the reference's masks
+            # (utils/loss.py:85,117) are all-true and the fused kernels do not evaluate them
+            if 0.0 <= float(self.ignore_index) <= 1.0:
+                raise RuntimeError("fused mode cannot honour an ignore_index inside [0,1]; use the strict mode")
+            n = pred.shape[0]
+            lab = _prep_label(label, pred.device, (n, int(out_size[0]), int(out_size[1])), "label")
+            loss = _FusedLoss.apply(pred, lab, tuple(out_size), self._mode, self.num_class, ratio,
+                                    self.global_batch, sink)
+        else:
+            _require_cuda_f32(prob, "prob")
+            self._check_classes(prob.shape[1])
+            n, _, h, w = prob.shape
+            lab = _prep_label(label, prob.device, (n, h, w), "label")
+            loss = _ProbLoss.apply(prob, lab, self._mode, self.num_class, ratio, self.ignore_index,
+                                   self.global_batch, sink)
+        self._publish(sink)
+        return loss
+
+
+class MaxSquareloss(_LossBase):
+    """``-mean(prob**2) / 2`` (``utils/loss.py:104-119``)."""
+    _mode = _lib.MODE_MAXSQUARE
+
+    def __init__(self, ignore_index=-1, num_class=19):
+        super().__init__(ignore_index, num_class)
+
+    def forward(self, pred, prob=None, out_size=None):
+        """
+        :param pred: predictions (N, C, H, W) -- unused in strict mode, as in the reference;
+                     in fused mode (``prob`` omitted) the low-resolution head logits (N, C, h, w)
+        :param prob: probability of pred (N, C, H, W)
+        :param out_size: (H, W) label resolution, fused mode only
+        :return: maximum squares loss (0-dim CUDA tensor)
+        """
+        return self._run(pred, prob, None, out_size, 0.0)
+
+
+class IW_MaxSquareloss(_LossBase):
+    """Image-wise weighted maximum squares loss (``utils/loss.py:69-102``)."""
+    _mode = _lib.MODE_IW
+
+    def __init__(self, ignore_index=-1, num_class=19, ratio=0.2):
+        super().__init__(ignore_index, num_class)
+        self.ratio = ratio
+
+    def forward(self, pred, prob=None, label=None, out_size=None):
+        """
+        :param pred: predictions (N, C, H, W) -- unused in strict mode; head logits in fused mode
+        :param prob: probability of pred (N, C, H, W)
+        :param label(optional): the map for counting label numbers (N, H, W)
+        :param out_size: (H, W) label resolution, fused mode only
+        :return: maximum squares loss with image-wise weighting factor (0-dim CUDA tensor)
+        """
+        return self._run(pred, prob, label, out_size, self.ratio)
+
+
+def maxsquare_from_logits(head_logits, out_size, global_batch=0):
+    """Functional fused MaxSquare loss from low-resolution head logits."""
+    crit = MaxSquareloss(-1, head_logits.shape[1])
+    crit.global_batch = global_batch
+    return crit(head_logits, out_size=out_size)
+
+
+def iw_maxsquare_from_logits(head_logits, out_size, ratio=0.2, label=None, global_batch=0, return_hist=False):
+    """Functional fused IW-MaxSquare loss from low-resolution head logits."""
+    crit = IW_MaxSquareloss(-1, head_logits.shape[1], ratio)
+    crit.global_batch = global_batch
+    loss = crit(head_logits, label=label, out_size=out_size)
+    return (loss, crit.last_hist) if return_hist else loss

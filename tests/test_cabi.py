@@ -1,0 +1,105 @@
+"""The C-ABI library loads and exports every symbol include/msq_b200.h declares; argument
+validation that needs no GPU.  CPU only (no kernel is launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from maxsquareloss_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "msq_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(msq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from maxsquareloss_b200 import _lib
+    decl = declared_symbols()
+    assert len(decl) >= 10
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/msq_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == decl, "python binding and header disagree on the symbol list"
+
+
+def test_abi_version_and_error_strings(lib):
+    assert lib.msq_abi_version() == 1
+    assert lib.msq_error_string(0) == b"success"
+    for code in (-1, -2, -3, -4):
+        assert lib.msq_error_string(code).startswith(b"msq:")
+
+
+def test_state_layout(lib):
+    from maxsquareloss_b200 import _lib
+    for n, c in [(1, 19), (2, 19), (8, 16), (3, 13), (1, 32)]:
+        lay = _lib.state_layout(n, c)
+        nc = n * c
+        assert lay.accum_bytes % 16 == 0 and lay.out_bytes % 16 == 0
+        assert lay.sumsq_off % 8 == 0 and lay.kept_off % 8 == 0 and lay.hist_off % 4 == 0
+        assert lay.hist_off >= lay.sumsq_off + 8 * nc
+        assert lay.accum_bytes >= lay.ticket_off + 4
+        assert lay.loss_off % 4 == 0 and lay.weights_off % 4 == 0 and lay.sum_out_off % 8 == 0
+        assert lay.stats_off % 8 == 0 and lay.stats_off >= lay.hist_out_off + 4 * nc
+        assert lay.out_bytes >= lay.stats_off + 8 * (1 + c)
+    bad = _lib.StateLayout()
+    assert lib.msq_state_layout_get(1, 33, ctypes.byref(bad)) == -1
+    assert lib.msq_state_layout_get(0, 19, ctypes.byref(bad)) == -1
+
+
+def test_argument_validation_without_gpu(lib):
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.msq_confusion_i64(None, None, 16, 19, None, None, None) == -1
+    assert lib.msq_confusion_i64(None, None, 16, 33, 8, None, None) == -1
+    assert lib.msq_confusion_i64(None, None, 0, 19, 8, None, None) == 0          # empty batch: no-op
+    assert lib.msq_confusion_logits_f32(None, None, 1, 19, 16, None, None) == -1
+    assert lib.msq_prob_fwd(0, None, 1, 19, 16, None, 0.2, -1, 0, None, None, None) == -1
+    assert lib.msq_prob_fwd(7, 16, 1, 19, 16, None, 0.2, -1, 0, 16, 16, None) == -1   # bad mode
+    assert lib.msq_prob_bwd(1, None, 1, 19, 16, -1, 0, None, None, None, None) == -1
+    assert lib.msq_fused_fwd(1, None, 1, 19, 4, 4, 8, 8, None, 0.2, 0, None, None, None) == -1
+    assert lib.msq_fused_fwd(1, 16, 1, 19, 8, 8, 4, 4, None, 0.2, 0, 16, 16, None) == -2   # downsampling
+    assert lib.msq_fused_bwd(1, None, 1, 19, 4, 4, 8, 8, 0, None, None, None, None) == -1
+    assert lib.msq_prob_fwd(0, 18, 1, 19, 16, None, 0.2, -1, 0, 16, 16, None) == -4       # misaligned prob
+    assert lib.msq_tune_set(b"no_such_knob", 1) == -1
+    assert lib.msq_tune_set(b"conf_agg", 1) == 0
+
+
+def test_host_side_refuses_cpu_tensors():
+    import torch
+    import maxsquareloss_b200 as msq
+    p = torch.softmax(torch.randn(1, 19, 4, 4), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.MaxSquareloss()(p, p)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.IW_MaxSquareloss()(p, p)
+    with pytest.raises(RuntimeError, match="out_size"):
+        msq.IW_MaxSquareloss()(p)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            msq.Eval(19)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from maxsquareloss_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "maxsquareloss_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
