@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""Benchmark of the MaxSquare hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], GTA5->Cityscapes target shape): per GPU a batch of
+2 images, 19 classes, DeepLabv2 head logits 65x129 upsampled to 512x1024.  A *step* is
+one pass of the hot path over that batch: fused IW-MaxSquare forward (bilinear upsample +
+softmax + per-image argmax histogram + image-wise weights + loss) and backward (dL/dlogits
+at 65x129).  Metric: Gpixel/s = label-resolution pixels / time.
+
+  value  device-resident inputs, kernels launched through the C ABI (ctypes)
+  e2e    the same step through the public Python API (IW_MaxSquareloss module +
+         autograd) with pinned HOST logits in and the loss + dL/dlogits back on the host
+
+Weak scaling: every rank owns its own 2 images (sharding by image); for N > 1 each step
+also all-reduces the packed [loss, class histogram] vector over NCCL, overlapped with
+the backward kernel.
+
+``--impl reference`` times the reference's algorithm on the host CPU (oracle/loss_port.py:
+F.interpolate -> softmax -> IW loss -> backward, all host threads).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "IW-MaxSquare fwd+bwd Gpixel/s"
+UNIT = "Gpixel/s"
+N_IMG, C, HW_LO, HW_OUT = 2, 19, (65, 129), (512, 1024)
+RATIO = 0.2
+LAMBDA_TARGET = 0.1                      # callers scale the loss before backward (solve_gta5.py:199)
+POOL = 128                               # distinct input buffers: 128 x 1.27 MB = 163 MB > 126 MB L2
+PX_PER_STEP = N_IMG * HW_OUT[0] * HW_OUT[1]
+WORKLOAD = ("cfg2 GTA5->Cityscapes target shape: IW-MaxSquare fwd+bwd, batch 2/GPU, 19 classes, "
+            "head logits 65x129 -> 512x1024, ratio 0.2")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        try:
+            mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            try:
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append(mhz)
+            for bit, name in list(self.BAD.items()) + list(self.NOTE.items()):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self._once()
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        self._once()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_chain_time(n_img, hw_lo, hw_out, iters, warm):
+    from maxsquareloss_b200 import synth
+    from oracle import loss_port
+    lo = synth.head_logits(n_img, C, hw_lo, 0, 5.0)
+    for _ in range(warm):
+        loss_port.chain_iw_maxsquare(lo, hw_out, C, RATIO, LAMBDA_TARGET)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        loss_port.chain_iw_maxsquare(lo, hw_out, C, RATIO, LAMBDA_TARGET)
+    return (time.perf_counter() - t0) / iters
+
+
+def cpu_baseline(budget_s=12.0):
+    """The reference's algorithm (oracle port, kind 'port') on this host's cores: a bounded
+    sample of the same workload (full-size steps until ~budget_s of CPU work)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    t1 = cpu_chain_time(N_IMG, HW_LO, HW_OUT, 1, 1)
+    iters = max(3, min(40, int(budget_s / max(t1, 1e-3))))
+    t = cpu_chain_time(N_IMG, HW_LO, HW_OUT, iters, 0)
+    return {"value": PX_PER_STEP / t / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{iters} full steps of the same workload (2x19x65x129 -> 512x1024), "
+                      f"F.interpolate+softmax+IW loss+backward, {t * 1e3:.0f} ms/step",
+            "ms_per_step": t * 1e3}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference is pure Python and cannot travel to the GPU box) on all host threads."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    t_full = cpu_chain_time(N_IMG, HW_LO, HW_OUT, 1, 1)
+    budget = 150.0
+    n_img, hw_lo, hw_out = N_IMG, HW_LO, HW_OUT
+    if (steps + warm) * t_full > budget:
+        # shrink the per-step sample (fewer images, then fewer rows) so that the run is bounded
+        frac = budget / ((steps + warm) * t_full)
+        if frac < 0.5:
+            n_img = 1
+            frac *= 2
+        if frac < 1.0:
+            rows_lo = max(9, int(HW_LO[0] * frac))
+            hw_lo = (rows_lo, HW_LO[1])
+            hw_out = ((rows_lo - 1) * 8, HW_OUT[1])
+    t = cpu_chain_time(n_img, hw_lo, hw_out, steps, warm)
+    px = n_img * hw_out[0] * hw_out[1]
+    val = px / t / 1e9
+    sample = (f"per step {n_img}x{C}x{hw_lo[0]}x{hw_lo[1]} -> {hw_out[0]}x{hw_out[1]} "
+              f"({px / PX_PER_STEP:.3f} of the workload's pixels), F.interpolate+softmax+IW loss+backward")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arm": "reference algorithm on host CPU (oracle port)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def time_loop(fn, iters, warm):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters          # ms per call
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import maxsquareloss_b200 as msq
+    from maxsquareloss_b200 import _lib, synth
+    from maxsquareloss_b200 import dist as mdist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    hbm_peak, peak_src = peaks()
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- inputs: POOL distinct batches of head logits, resident in HBM (and a pinned host copy)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_lo = N_IMG * C * HW_LO[0] * HW_LO[1]
+    lo_pool = torch.randn(POOL, N_IMG, C, *HW_LO, generator=g, device=dev) * 5.0
+    grad_pool = torch.empty_like(lo_pool)
+    go = torch.full((), LAMBDA_TARGET, device=dev)
+    lay = _lib.state_layout(N_IMG, C)
+    accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev)
+    outs = torch.empty(POOL, lay.out_bytes, dtype=torch.uint8, device=dev)
+    stats_views = [outs[i, lay.stats_off:lay.stats_off + 8 * (1 + C)].view(torch.float64) for i in range(POOL)]
+    n_norm = N_IMG * world
+    lo_ptrs = [lo_pool[i].data_ptr() for i in range(POOL)]
+    gr_ptrs = [grad_pool[i].data_ptr() for i in range(POOL)]
+    out_ptrs = [outs[i].data_ptr() for i in range(POOL)]
+    acc_ptr, go_ptr = accum.data_ptr(), go.data_ptr()
+    MODE = _lib.MODE_IW
+    h, w = HW_LO
+    H, W = HW_OUT
+
+    def fwd(i):
+        j = i % POOL
+        rc = lib.msq_fused_fwd(MODE, lo_ptrs[j], N_IMG, C, h, w, H, W, None, RATIO, n_norm, acc_ptr, out_ptrs[j], stream)
+        if rc:
+            _lib.check(rc)
+
+    def bwd(i):
+        j = i % POOL
+        rc = lib.msq_fused_bwd(MODE, lo_ptrs[j], N_IMG, C, h, w, H, W, n_norm, out_ptrs[j], go_ptr, gr_ptrs[j], stream)
+        if rc:
+            _lib.check(rc)
+
+    pending = []
+
+    def step(i):
+        fwd(i)
+        if world > 1:      # one small all-reduce per step, overlapped with the backward kernel
+            pending.append(dist.all_reduce(stats_views[i % POOL], async_op=True))
+        bwd(i)
+        if world > 1 and len(pending) >= 2:
+            pending.pop(0).wait()
+
+    # ---- warm-up: at least W steps and at least ~0.3 s so the clocks are up
+    t0 = time.perf_counter()
+    i = 0
+    min_warm_s = float(os.environ.get("MSQ_BENCH_MIN_WARM_S", "0.3"))     # 0 under ncu
+    while i < warm or time.perf_counter() - t0 < min_warm_s:
+        step(i)
+        i += 1
+        if i % 256 == 0:
+            torch.cuda.synchronize()
+    for wk in pending:
+        wk.wait()
+    pending.clear()
+    torch.cuda.synchronize()
+
+    # ---- timed region: EXACTLY `steps` steps, barrier + synchronize on both sides, max over ranks
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        step(i)
+    for wk in pending:
+        wk.wait()
+    pending.clear()
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / steps
+    value = world * PX_PER_STEP / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: public Python API, pinned host buffers, H2D + D2H inside the timed region
+    crit = msq.IW_MaxSquareloss(-1, C, RATIO)
+    crit.global_batch = n_norm
+    e2e_pool = min(POOL, 16)
+    host_in = [lo_pool[i].cpu().pin_memory() for i in range(e2e_pool)]
+    host_grad = torch.empty(N_IMG, C, *HW_LO).pin_memory()
+    host_loss = torch.empty(()).pin_memory()
+    dev_in = torch.empty(N_IMG, C, *HW_LO, device=dev)
+    cur = torch.cuda.current_stream()
+
+    def e2e_step(i):
+        dev_in.copy_(host_in[i % e2e_pool], non_blocking=True)                 # H2D
+        x = dev_in.detach().requires_grad_(True)
+        loss = crit(x, out_size=HW_OUT)
+        (LAMBDA_TARGET * loss).backward()
+        host_grad.copy_(x.grad, non_blocking=True)                              # D2H
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        cur.synchronize()                                                       # the host reads the result
+        return host_loss
+
+    e2e_steps = steps
+    for i in range(max(warm, 20)):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * PX_PER_STEP * e2e_steps / e2e_s / 1e9
+    last_loss = float(host_loss.item())
+
+    # ---- per-kernel roofline numbers (rank 0 reports; every rank runs them to stay in step)
+    kit = max(50, min(steps, 400))
+    lo_bytes = 4.0 * n_lo
+    t_fwd = time_loop(fwd, kit, 20)
+    t_bwd = time_loop(bwd, kit, 20)
+    kernels = [
+        {"kernel": "fused_fwd_kernel<19,IW>", "bound": "issue/MUFU (not HBM)", "algorithmic_bytes": lo_bytes,
+         "ms": t_fwd, "achieved_GBps": lo_bytes / t_fwd / 1e6, "frac_of_hbm": lo_bytes / t_fwd / 1e6 / hbm_peak,
+         "gpixel_per_s": PX_PER_STEP / t_fwd / 1e6},
+        {"kernel": "fused_bwd_kernel<19,IW> (+memset of dL/dlogits)", "bound": "issue/MUFU (not HBM)",
+         "algorithmic_bytes": 2 * lo_bytes, "ms": t_bwd, "achieved_GBps": 2 * lo_bytes / t_bwd / 1e6,
+         "frac_of_hbm": 2 * lo_bytes / t_bwd / 1e6 / hbm_peak, "gpixel_per_s": PX_PER_STEP / t_bwd / 1e6},
+    ]
+    extra = {}
+    if rank == 0 and not args.skip_secondary:
+        kernels += secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit)
+        extra["maxsquare"] = maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, acc_ptr, go_ptr, n_norm, stream, kit)
+    dom = max(kernels[:2], key=lambda k: k["ms"])
+    roofline = {"bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom["achieved_GBps"] / hbm_peak, "traffic": None, "kernel": dom["kernel"],
+                "peak_source": peak_src,
+                "note": "the fused kernels move 3.65 algorithmic B/pixel and are FP32-issue/MUFU bound by design "
+                        "(SURVEY.md 8d); the HBM-bound kernels of the path are listed under 'kernels'"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "images_per_gpu": N_IMG, "global_batch": n_norm,
+                           "l2_policy": f"inputs rotate over {POOL} distinct logits buffers "
+                                        f"({POOL * lo_bytes / 1e6:.0f} MB > 126 MB L2); outputs likewise",
+                           "parallelism": f"image-sharded x{world}" + (", 1 NCCL all-reduce of [loss,hist] per step "
+                                                                        "overlapped with backward" if world > 1 else "")},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lo_bytes),
+                        "d2h_bytes_per_step": int(lo_bytes) + 4, "steps": e2e_steps,
+                        "ms_per_step": e2e_s / e2e_steps * 1e3,
+                        "how": "IW_MaxSquareloss(head_logits, out_size) + backward via the Python API; pinned host "
+                               "logits H2D, dL/dlogits + loss D2H, stream sync every step", "last_loss": last_loss},
+                "gpu_launches": 2 * steps,
+                "roofline": roofline, "kernels": kernels}
+        line.update(extra)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit):
+    """The HBM-bound kernels of the path, each on buffers that exceed L2."""
+    out = []
+    kit = min(kit, 100)
+    npx = PX_PER_STEP
+    # strict drop-in on full-resolution prob (2 x 19 x 512 x 1024 fp32 = 159 MB per buffer)
+    probs = [torch.softmax(torch.randn(N_IMG, C, *HW_OUT, device=dev) * 3, 1) for _ in range(2)]
+    grads = [torch.empty_like(p) for p in probs]
+    lay = _lib.state_layout(N_IMG, C)
+    accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev)
+    o = torch.empty(lay.out_bytes, dtype=torch.uint8, device=dev)
+    go = torch.ones((), device=dev)
+    hw = HW_OUT[0] * HW_OUT[1]
+    for mode, name in ((_lib.MODE_IW, "IW"), (_lib.MODE_MAXSQUARE, "MaxSquare")):
+        f = lambda i: lib.msq_prob_fwd(mode, probs[i % 2].data_ptr(), N_IMG, C, hw, None, RATIO, -1, 0,
+                                       accum.data_ptr(), o.data_ptr(), stream)
+        b = lambda i: lib.msq_prob_bwd(mode, probs[i % 2].data_ptr(), N_IMG, C, hw, -1, 0, o.data_ptr(),
+                                       go.data_ptr(), grads[i % 2].data_ptr(), stream)
+        tf, tb = time_loop(f, kit, 5), time_loop(b, kit, 5)
+        for nm, t, byt in ((f"prob_fwd_kernel<19,{name}>", tf, 4.0 * C * npx), (f"prob_bwd_kernel<19,{name}>", tb, 8.0 * C * npx)):
+            out.append({"kernel": nm, "bound": "hbm", "algorithmic_bytes": byt, "ms": t, "achieved_GBps": byt / t / 1e6,
+                        "frac_of_hbm": byt / t / 1e6 / hbm_peak, "gpixel_per_s": npx / t / 1e6})
+    del probs, grads
+    # confusion matrix, source-batch shape of cfg 2 (2 x 720 x 1280), buffers rotate past L2
+    n_src, hw_src = 2, (720, 1280)
+    pool = 8
+    gts = [synth.blocky_labels(n_src, hw_src, C, 100 + i).to(dev) for i in range(pool)]
+    prs = [synth.noisy_prediction(gts[i].cpu(), C, 100 + i).to(dev) for i in range(pool)]
+    cm = torch.zeros(C * C + 1, dtype=torch.int64, device=dev)
+    px_src = n_src * hw_src[0] * hw_src[1]
+    f = lambda i: lib.msq_confusion_i64(gts[i % pool].data_ptr(), prs[i % pool].data_ptr(), px_src, C, cm.data_ptr(),
+                                        cm.data_ptr() + 8 * C * C, stream)
+    t = time_loop(f, kit, 5)
+    out.append({"kernel": "confusion_i64_kernel (blocky gt, 30% noisy pred)", "bound": "hbm", "algorithmic_bytes": 16.0 * px_src,
+                "ms": t, "achieved_GBps": 16.0 * px_src / t / 1e6, "frac_of_hbm": 16.0 * px_src / t / 1e6 / hbm_peak,
+                "gpixel_per_s": px_src / t / 1e6})
+    lgs = [torch.randn(n_src, C, *hw_src, device=dev) for _ in range(2)]
+    f = lambda i: lib.msq_confusion_logits_f32(gts[i % pool].data_ptr(), lgs[i % 2].data_ptr(), n_src, C,
+                                               hw_src[0] * hw_src[1], cm.data_ptr(), stream)
+    t = time_loop(f, kit, 5)
+    byt = (4.0 * C + 8) * px_src
+    out.append({"kernel": "confusion_logits_kernel<19> (argmax fused)", "bound": "hbm", "algorithmic_bytes": byt, "ms": t,
+                "achieved_GBps": byt / t / 1e6, "frac_of_hbm": byt / t / 1e6 / hbm_peak, "gpixel_per_s": px_src / t / 1e6})
+    return out
+
+
+def maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, acc_ptr, go_ptr, n_norm, stream, kit):
+    """Same step with MaxSquareloss instead of the IW loss (cfg 2 as literally written)."""
+    h, w = HW_LO
+    H, W = HW_OUT
+
+    def st(i):
+        j = i % POOL
+        lib.msq_fused_fwd(_lib.MODE_MAXSQUARE, lo_ptrs[j], N_IMG, C, h, w, H, W, None, 0.0, n_norm, acc_ptr, out_ptrs[j], stream)
+        lib.msq_fused_bwd(_lib.MODE_MAXSQUARE, lo_ptrs[j], N_IMG, C, h, w, H, W, n_norm, out_ptrs[j], go_ptr, gr_ptrs[j], stream)
+    t = time_loop(st, kit, 20)
+    return {"metric": "MaxSquare fwd+bwd Gpixel/s", "value": PX_PER_STEP / t / 1e6, "ms_per_step": t}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
+    ap.add_argument("--skip-secondary", action="store_true", help="omit the secondary kernel table")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
