@@ -51,17 +51,19 @@ const char* msq_error_string(int code);
  * msq_state_layout_get):
  *
  * ACCUMULATORS (`accum`, accum_bytes): must be ZERO when a *_fwd call starts and
- * are zero again when that call's kernels have finished (the last CTA to finish
- * finalises and re-zeroes them), so ONE zero-initialised buffer per stream can
- * be reused forever without a memset.  Not shareable between streams.
- *   sumsq  uint64[N*C]  sum over pixels of q = sum_c p_c^2 in 2^-32 fixed point,
+ * are zero again when that call's kernels have finished (the finalisation kernel
+ * that every *_fwd call enqueues re-zeroes them), so ONE zero-initialised buffer
+ * per stream can be reused forever without a memset.  Not shareable between streams.
+ *   sumsq  uint64[R][N*C] sum over pixels of q = sum_c p_c^2 in 2^-32 fixed point,
  *                       bucketed by the pixel's argmax class (IW) or in bucket 0
  *                       of each image (MaxSquare).  Integer, hence
  *                       order-independent: the loss is bit-reproducible.
+ *                       R = 16 replicas (CTA b adds into replica b % R) keep
+ *                       same-address L2 atomics off the critical path.
  *   kept   uint64       number of prob elements != ignore_index (MaxSquare mean)
- *   hist   uint32[N*C]  per-image class histogram being accumulated
+ *   hist   uint32[R][N*C] per-image class histogram being accumulated
  *   flags  uint32       bit0: a non-finite value was seen (loss becomes NaN)
- *   ticket uint32       CTA completion counter
+ *   ticket uint32       reserved
  *
  * OUTPUTS (`out`, out_bytes): written by the forward, read by the backward.
  *   sum_out   float64[N]   per-image sum of q (diagnostics / multi-GPU reduction)

@@ -8,7 +8,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libmsq_b200.so")
+LIB_PATH = os.environ.get("MSQ_B200_LIB") or os.path.join(_PKG, "lib", "libmsq_b200.so")   # override: A/B builds
 
 MAX_CLASSES = 32
 MODE_MAXSQUARE = 0

@@ -14,6 +14,10 @@ constexpr int kSMs = 148;                       // B200: 2 dies x 74 SMs
 constexpr float kFix = 4294967296.0f;           // 2^32: fixed-point scale of q = sum_c p_c^2
 constexpr double kInvFix = 1.0 / 4294967296.0;
 constexpr unsigned kFlagNonFinite = 1u;
+// The per-image accumulators are replicated kRep times (CTA b adds into replica b % kRep):
+// a few hundred CTAs finishing together would otherwise queue on the same 2*N*C L2
+// addresses (same-address L2 atomics serialise at ~10 ns each on this chip).
+constexpr int kRep = 16;
 
 // Carved view of the caller's state buffer (see msq_state_layout in the header).
 struct State {
@@ -35,9 +39,9 @@ __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + 
 inline msq_state_layout make_layout(int n, int c) {
     msq_state_layout L;
     int64_t nc = (int64_t)n * c, off = 0;
-    L.sumsq_off = off;  off += nc * 8;                 // 8-byte members first
+    L.sumsq_off = off;  off += nc * 8 * kRep;          // 8-byte members first
     L.kept_off = off;   off += 8;
-    L.hist_off = off;   off += nc * 4;
+    L.hist_off = off;   off += nc * 4 * kRep;
     L.flags_off = off;  off += 4;
     L.ticket_off = off; off += 4;
     L.accum_bytes = align_up(off, 16);
@@ -135,84 +139,15 @@ __device__ __forceinline__ float iw_weight(float hist, float total, float r32, f
 }
 
 
-// ---------------------------------------------------------------------------------
-// Finalisation, run by every thread of the LAST CTA to finish (ticket pattern):
-// turns the integer accumulators into the reference's scalar, the per-image
-// weights and the final histogram, then re-zeroes the accumulators so the state
+// Finalisation kernel (api.cu), launched on the same stream right after a forward kernel:
+// sums the replicas, turns the integer accumulators into the reference's scalar, the
+// per-image weights and the final histogram, and re-zeroes the accumulators so the
 // buffer is ready for the next call without a memset.
 //   IW        (utils/loss.py:95,100):  loss = -(1/(Nn*C)) sum_n sum_k w_nk * S_nk
 //   MaxSquare (utils/loss.py:118):     loss = -(sum q) / (2 * kept)
 // Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ bool take_ticket_is_last(unsigned int* ticket, unsigned total_ctas) {
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(ticket, 1u);
-        s_last = (t == total_ctas - 1);
-    }
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last;
-}
-
-__device__ inline void finalize_loss(const State& st, int mode, int n, int C, float r32, float omr32,
-                                     int n_norm, unsigned long long kept_dense) {
-    __shared__ double s_red[32];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int nc = n * C;
-    volatile unsigned int* vhist = st.hist;
-    volatile unsigned long long* vsum = st.sumsq;
-    double part = 0.0;
-    for (int idx = tid; idx < nc; idx += nthr) {
-        const int img = idx / C;
-        const unsigned hcnt = vhist[idx];
-        const double S = (double)vsum[idx] * kInvFix;
-        float wgt = 1.0f;
-        if (mode == MSQ_MODE_IW) {
-            unsigned total = 0;
-            for (int k = 0; k < C; ++k) total += vhist[img * C + k];
-            wgt = iw_weight((float)hcnt, (float)total, r32, omr32);
-            part += (double)wgt * S;
-        } else {
-            part += S;
-        }
-        st.weights[idx] = wgt;
-        st.hist_out[idx] = (int)hcnt;
-    }
-    for (int img = tid; img < n; img += nthr) {
-        double s = 0.0;
-        for (int k = 0; k < C; ++k) s += (double)vsum[img * C + k] * kInvFix;
-        st.sum_out[img] = s;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0) s_red[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int i = 0; i < (nthr + 31) / 32; ++i) tot += s_red[i];
-        const unsigned long long kept_local = (kept_dense != 0ull) ? kept_dense : *((volatile unsigned long long*)st.kept);
-        const double scale = (double)n_norm / (double)n;
-        double loss;
-        if (mode == MSQ_MODE_IW) loss = -tot / ((double)n_norm * (double)C);
-        else loss = -tot / (2.0 * (double)kept_local * scale);
-        if (*((volatile unsigned int*)st.flags) & kFlagNonFinite) loss = __longlong_as_double(0x7ff8000000000000LL);
-        *st.loss = (float)loss;
-        *st.kept_out = kept_local;
-        st.stats[0] = loss;
-    }
-    for (int k = tid; k < C; k += nthr) {
-        unsigned long long tot = 0ull;
-        for (int img = 0; img < n; ++img) tot += vhist[img * C + k];
-        st.stats[1 + k] = (double)tot;
-    }
-    __syncthreads();
-    // self-clean the accumulators (stream order makes this visible to the next call)
-    for (int idx = tid; idx < nc; idx += nthr) { st.hist[idx] = 0u; st.sumsq[idx] = 0ull; }
-    if (tid == 0) { *st.kept = 0ull; *st.flags = 0u; *st.ticket = 0u; }
-}
+int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
+                    unsigned long long kept_dense, cudaStream_t stream);
 
 }  // namespace msq
 

@@ -27,6 +27,12 @@
 namespace msq {
 
 constexpr int kTW = 128;                        // output columns (= threads) per CTA
+#ifndef MSQ_FWD_MINB
+#define MSQ_FWD_MINB 4                          // co-resident CTAs per SM the forward is compiled for
+#endif
+#ifndef MSQ_BWD_MINB
+#define MSQ_BWD_MINB 4
+#endif
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNearTie = 2.384185791015625e-07f;   // 2^-22, see resolve_ties
 constexpr float kPadLogit = -1.0e30f;           // logits of padded classes (C < CT)
@@ -74,54 +80,79 @@ __device__ __noinline__ int resolve_ties(const float* z, float m) {
     return k;
 }
 
-// Per-pixel softmax statistics from the interpolated logits z[]:
-//   e[c] = 2^((z_c - m) log2 e), inv_s = 1/sum e, q = sum_c p_c^2, returns argmax class.
+// Classes are processed two at a time with Blackwell's packed fp32x2 instructions
+// (fma.rn.f32x2 / mul.f32x2 / add.f32x2, sm_100+): the kernels are instruction-issue
+// bound, and one FFMA2 does the work of two FFMAs with identical IEEE rounding per
+// lane, so bit-exactness of the interpolated logits is unaffected.  Class c lives in
+// lane (c & 1) of pair (c >> 1); an odd class count leaves one padding lane.
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float lane_of(const float2& v, int c) { return (c & 1) ? v.y : v.x; }
+
+// Per-pixel softmax statistics from the interpolated logits z[] (pairs):
+//   e[c] = 2^((z_c - m) log2 e), inv_s = 1/s with s = sum e, q = sum_c p_c^2, qs = q*s;
+//   returns the argmax class.
 template <int CT, bool NEED_ARG>
-__device__ __forceinline__ int pixel_stats(const float (&z)[CT], float (&e)[CT], float& inv_s, float& q) {
-    float m = z[0];
+__device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], float2 (&e)[(CT + 1) / 2], float& inv_s,
+                                           float& q, float& qs) {
+    constexpr int CP = (CT + 1) / 2;
+    float m = z[0].x;
 #pragma unroll
-    for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
+    for (int c = 1; c < CT; ++c) m = fmaxf(m, lane_of(z[c >> 1], c));
     int k = 0;
     if (NEED_ARG) {
         const float thr = m - kNearTie;
         unsigned mask = 0u;
 #pragma unroll
-        for (int c = 0; c < CT; ++c) mask |= (z[c] >= thr) ? (1u << c) : 0u;
+        for (int c = 0; c < CT; ++c)                    // one FSETP + one predicated LOP3 per class
+            asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                : "+r"(mask) : "f"(lane_of(z[c >> 1], c)), "f"(thr), "r"(1u << c));
         k = __ffs(mask) - 1;
         if (mask & (mask - 1u)) {                       // more than one class within 2^-22 of the max
+            asm volatile("" ::: "memory");              // keep the spill of z[] inside this cold branch
             float zl[CT];
 #pragma unroll
-            for (int c = 0; c < CT; ++c) zl[c] = z[c];
+            for (int c = 0; c < CT; ++c) zl[c] = lane_of(z[c >> 1], c);
             k = resolve_ties<CT>(zl, m);
         }
         if (k < 0) k = 0;                               // NaN logits: reference yields NaN loss anyway
     }
-    const float nm = -m * kLog2e;
-    float s = 0.f, ss = 0.f;
+    const float2 l2e = splat(kLog2e), nm = splat(-m * kLog2e);
+    float2 s2 = make_float2(0.f, 0.f), ss2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < CT; ++c) {
-        e[c] = ex2_approx(fmaf(z[c], kLog2e, nm));
-        s += e[c];
-        ss = fmaf(e[c], e[c], ss);
+    for (int p = 0; p < CP; ++p) {
+        const float2 t = __ffma2_rn(z[p], l2e, nm);
+        e[p] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        s2 = __fadd2_rn(s2, e[p]);
+        ss2 = __ffma2_rn(e[p], e[p], ss2);
     }
+    const float s = s2.x + s2.y, ss = ss2.x + ss2.y;
     inv_s = rcp_approx(s);
-    q = ss * inv_s * inv_s;
+    qs = ss * inv_s;            // q * s
+    q = qs * inv_s;
     return k;
 }
 
-// Column bookkeeping shared by both kernels.
+// ---------------------------------------------------------------------------------
+// Work partition.  The output is cut into "row units": one unit = one output row of
+// one kTW-wide column tile of one image, numbered u = (n*TX + tx)*H + y.  The grid
+// has exactly as many CTAs as fit on the chip at once (148 x occupancy, one wave, no
+// tail) and CTA b owns the contiguous unit range [b*U/G, (b+1)*U/G): every CTA gets
+// the same number of rows to within one.  A range is walked as 1..2 "segments"
+// (it may cross a column-tile boundary); per segment the low-res tile is staged in
+// shared memory and each thread walks its column down the rows.
+// ---------------------------------------------------------------------------------
 struct Strip {
-    int n, xs, xe, ys, ye;        // output extent of this CTA
+    int n, xs, xe, ys, ye;        // output extent of this segment
     int c_lo, r_lo, nc, nr;       // low-res tile origin / extent
 };
 
-__device__ __forceinline__ Strip make_strip(const FusedGeo& g) {
+__device__ __forceinline__ Strip make_strip(const FusedGeo& g, int col, int TX, int ys, int ye) {
     Strip s;
-    s.n = blockIdx.z;
-    s.xs = blockIdx.x * kTW;
+    s.n = col / TX;
+    s.xs = (col - s.n * TX) * kTW;
     s.xe = min(g.W, s.xs + kTW);
-    s.ys = blockIdx.y * g.R;
-    s.ye = min(g.H, s.ys + g.R);
+    s.ys = ys;
+    s.ye = ye;
     int i0, i1;
     float l0, l1;
     src_index(g.sx, s.xs, g.w, i0, i1, l0, l1);
@@ -132,141 +163,206 @@ __device__ __forceinline__ Strip make_strip(const FusedGeo& g) {
     s.r_lo = i0;
     src_index(g.sy, s.ye - 1, g.h, i0, i1, l0, l1);
     s.nr = i1 - s.r_lo + 1;
+    if (s.nc > g.ncp || s.nr > g.nrm) __trap();      // host sized the tile from the same arithmetic
     return s;
 }
 
-// stage the low-res tile [C][nr][nc] (pitches nrm, ncp) in shared memory
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// Stage the low-res tile [C][nr][nc] (pitches nrm, ncp) in shared memory with
+// cp.async (LDGSTS): every element is in flight at once, no register staging.
+// Thread t owns tile element (t / nc, t % nc) of every class: one integer division per
+// segment, then one cp.async per class.
 __device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict__ lo, const FusedGeo& g,
                                           const Strip& s) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int rows = g.C * s.nr;
+    const int cells = s.nr * s.nc;
+    const int hw = g.h * g.w, cstride = g.nrm * g.ncp;
     const float* base = lo + ((long long)s.n * g.C * g.h + s.r_lo) * g.w + s.c_lo;
-    for (int row = wid; row < rows; row += nw) {
-        const int c = row / s.nr, r = row - c * s.nr;
-        const float* src = base + ((long long)c * g.h + r) * g.w;
-        float* dst = s_tile + (c * g.nrm + r) * g.ncp;
-        for (int j = lane; j < s.nc; j += 32) dst[j] = __ldg(src + j);
+    for (int t = threadIdx.x; t < cells; t += kTW) {
+        const int r = t / s.nc, j = t - r * s.nc;
+        const float* src = base + r * g.w + j;
+        float* dst = s_tile + r * g.ncp + j;
+#pragma unroll 4
+        for (int c = 0; c < g.C; ++c) cp_async4(dst + c * cstride, src + (long long)c * hw);
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // t_r[c] = fma(A[c][r][x0], lx0, A[c][r][x1] * lx1)   (horizontal pass of ATen's formula)
-template <int CT>
-__device__ __forceinline__ void hline(float (&Hx)[CT], const float* s_tile, const FusedGeo& g, int rr, int j0,
-                                      int j1, float lx0, float lx1) {
+template <int CT, bool PAD>
+__device__ __forceinline__ void hline(float2 (&Hx)[(CT + 1) / 2], const float* s_tile, const FusedGeo& g, int rr,
+                                      int j0, int j1, float lx0, float lx1) {
+    constexpr int CP = (CT + 1) / 2;
+    const float* row = s_tile + rr * g.ncp;
+    const int cstride = g.nrm * g.ncp;
+    const float2 l0 = splat(lx0), l1 = splat(lx1);
 #pragma unroll
-    for (int c = 0; c < CT; ++c) {
-        if (c < g.C) {
-            const float* row = s_tile + (c * g.nrm + rr) * g.ncp;
-            Hx[c] = __fmaf_rn(row[j0], lx0, __fmul_rn(row[j1], lx1));
-        } else {
-            Hx[c] = kPadLogit;
-        }
+    for (int p = 0; p < CP; ++p) {
+        const int c0 = 2 * p, c1 = 2 * p + 1;
+        const bool in0 = !PAD || c0 < g.C;
+        const bool in1 = (c1 < CT) && (!PAD || c1 < g.C);
+        const float2 a = make_float2(in0 ? row[c0 * cstride + j0] : kPadLogit, in1 ? row[c1 * cstride + j0] : kPadLogit);
+        const float2 b = make_float2(in0 ? row[c0 * cstride + j1] : kPadLogit, in1 ? row[c1 * cstride + j1] : kPadLogit);
+        Hx[p] = __ffma2_rn(a, l0, __fmul2_rn(b, l1));
     }
 }
 
+constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
+
 // ------------------------------------------------------------------ K1: forward
-template <int CT, bool IW, bool HAS_LABEL>
-__global__ void __launch_bounds__(kTW, 6)
-fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, const int64_t* __restrict__ label, float r32,
-                 float omr32, int n_norm, State st) {
-    extern __shared__ float s_tile[];
-    __shared__ unsigned s_hist[MSQ_MAX_CLASSES];
-    __shared__ unsigned long long s_sum[MSQ_MAX_CLASSES];
-    __shared__ unsigned s_flags;
-    const int tid = threadIdx.x;
-    if (tid < MSQ_MAX_CLASSES) { s_hist[tid] = 0u; s_sum[tid] = 0ull; }
-    if (tid == 0) s_flags = 0u;
-    const Strip sp = make_strip(g);
-    load_tile(s_tile, lo, g, sp);
-    __syncthreads();
-
-    const bool active = (sp.xs + tid) < sp.xe;
-    const int x = active ? sp.xs + tid : sp.xe - 1;
-    int x0, x1;
-    float lx0, lx1;
-    src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
-    const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
-
-    float Ha[CT], Hb[CT];
-    int ra = -1, rb = -1;
-    int run_k = -1;
-    unsigned run_cnt = 0u;
-    float run_q = 0.f;
-    auto flush = [&]() {
-        if (run_k >= 0 && run_cnt) {
-            if (IW && !HAS_LABEL) atomicAdd(&s_hist[run_k], run_cnt);
-            if (!(fabsf(run_q) < 3.0e38f)) atomicOr(&s_flags, kFlagNonFinite);
-            if (IW) atomicAdd(&s_sum[run_k], to_fix(run_q));
-        }
-    };
-
-    for (int y = sp.ys; y < sp.ye; ++y) {
-        int y0, y1;
-        float ly0, ly1;
-        src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
-        if (y0 != ra) {
-            if (y0 == rb) {
-#pragma unroll
-                for (int c = 0; c < CT; ++c) Ha[c] = Hb[c];
-            } else {
-                hline<CT>(Ha, s_tile, g, y0 - sp.r_lo, j0, j1, lx0, lx1);
-            }
-            ra = y0;
-        }
-        if (y1 != rb) {
-            if (y1 == ra) {
-#pragma unroll
-                for (int c = 0; c < CT; ++c) Hb[c] = Ha[c];
-            } else {
-                hline<CT>(Hb, s_tile, g, y1 - sp.r_lo, j0, j1, lx0, lx1);
-            }
-            rb = y1;
-        }
-        float z[CT], e[CT];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) z[c] = __fmaf_rn(Ha[c], ly0, __fmul_rn(Hb[c], ly1));
-        float inv_s, q;
-        const int k = pixel_stats<CT, IW>(z, e, inv_s, q);
-        if (active) {
-            if (IW) {
-                if (HAS_LABEL) {
-                    const long long lv = label[((long long)sp.n * g.H + y) * g.W + x];
-                    if (lv >= 0 && lv < g.C) atomicAdd(&s_hist[(int)lv], 1u);
-                }
-                if (k == run_k) { run_cnt++; run_q += q; }
-                else { flush(); run_k = k; run_cnt = 1u; run_q = q; }
-            } else {
-                run_k = 0; run_cnt++; run_q += q;
-            }
-        }
-    }
+// IW: every thread keeps, per class, a private packed accumulator in shared memory
+//     (count << 48 | sum of q in 2^-32 fixed point): a class change along the column
+//     costs one conflict-free LDS.64/STS.64 pair, no atomics.  The buckets are reduced
+//     by warp shuffles at the end of the segment and merged with one global atomic per
+//     class and warp.
+template <int CT, bool PAD, bool IW, bool HAS_LABEL>
+__global__ void __launch_bounds__(kTW, MSQ_FWD_MINB)
+fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, const int64_t* __restrict__ label,
+                 State st) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* s_bkt = (unsigned long long*)s_raw;                   // [C][kTW]   (IW only)
+    float* s_tile = (float*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));      // [C][nrm][ncp]
+    __shared__ unsigned s_lab[MSQ_MAX_CLASSES];                               // label= histogram
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
     if (IW) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
+    }
+    if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
+
+    // units < 2^31 (checked on the host): 32-bit divisions only
+    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
+    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
+    unsigned long long ms_acc = 0ull;
+    bool bad = false;
+    while (u < u_end) {
+        const unsigned col = u / (unsigned)g.H;
+        const int ys = (int)(u - col * (unsigned)g.H);
+        const int ye = (int)min((unsigned)g.H, (unsigned)ys + (u_end - u));
+        u += (unsigned)(ye - ys);
+        const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
+        __syncthreads();                                   // previous segment done with s_tile / buckets zeroed
+        load_tile(s_tile, lo, g, sp);
+        __syncthreads();
+
+        const bool active = (sp.xs + tid) < sp.xe;
+        const int x = active ? sp.xs + tid : sp.xe - 1;
+        int x0, x1;
+        float lx0, lx1;
+        src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
+        const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
+
+        constexpr int CP = (CT + 1) / 2;
+        float2 Ha[CP], Hb[CP];
+        int ra = -1, rb = -1;
+        int run_k = -1;
+        unsigned run_cnt = 0u;
+        float run_q = 0.f;
+        auto flush = [&]() {
+            if (run_cnt) {
+                bad |= !(fabsf(run_q) < 3.0e38f);
+                if (IW) {
+                    const unsigned long long inc = to_fix(run_q) + (HAS_LABEL ? 0ull : ((unsigned long long)run_cnt << 48));
+                    s_bkt[run_k * kTW + tid] += inc;
+                } else {
+                    ms_acc += to_fix(run_q);
+                }
+            }
+        };
+
+        for (int y = sp.ys; y < sp.ye; ++y) {
+            int y0, y1;
+            float ly0, ly1;
+            src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
+            if (y0 != ra) {
+                if (y0 == rb) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) Ha[p] = Hb[p];
+                } else {
+                    hline<CT, PAD>(Ha, s_tile, g, y0 - sp.r_lo, j0, j1, lx0, lx1);
+                }
+                ra = y0;
+            }
+            if (y1 != rb) {
+                if (y1 == ra) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) Hb[p] = Ha[p];
+                } else {
+                    hline<CT, PAD>(Hb, s_tile, g, y1 - sp.r_lo, j0, j1, lx0, lx1);
+                }
+                rb = y1;
+            }
+            float2 z[CP], e[CP];
+            {
+                const float2 w0 = splat(ly0), w1 = splat(ly1);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+            }
+            float inv_s, q, qs;
+            const int k = pixel_stats<CT, IW>(z, e, inv_s, q, qs);
+            if (active) {
+                if (IW) {
+                    if (HAS_LABEL) {
+                        const long long lv = label[((long long)sp.n * g.H + y) * g.W + x];
+                        if (lv >= 0 && lv < g.C) atomicAdd(&s_lab[(int)lv], 1u);
+                    }
+                    if (k == run_k) { run_cnt++; run_q += q; }
+                    else { flush(); run_k = k; run_cnt = 1u; run_q = q; }
+                } else {
+                    run_k = 0; run_cnt++; run_q += q;
+                }
+            }
+        }
         flush();
-    } else {
-        // MaxSquare: one bucket; reduce the strip in registers first
-        if (!(fabsf(run_q) < 3.0e38f)) atomicOr(&s_flags, kFlagNonFinite);
-        unsigned long long v = warp_sum_u64(run_cnt ? to_fix(run_q) : 0ull);
-        if ((tid & 31) == 0 && v) atomicAdd(&s_sum[0], v);
+
+        if (IW) {
+            // reduce the private buckets of this segment: warp w owns classes w, w+4, ...
+            __syncthreads();
+            for (int c = wid; c < g.C; c += kTW / 32) {
+                unsigned cnt = 0u;
+                unsigned long long sum = 0ull;
+#pragma unroll
+                for (int t = 0; t < kTW / 32; ++t) {
+                    const unsigned long long v = s_bkt[c * kTW + t * 32 + lane];
+                    s_bkt[c * kTW + t * 32 + lane] = 0ull;
+                    cnt += (unsigned)(v >> 48);
+                    sum += v & kBktMask;
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                sum = warp_sum_u64(sum);
+                if (lane == 0) {
+                    if (HAS_LABEL) cnt = s_lab[c];
+                    if (cnt) atomicAdd(&st.hist[rep_off + sp.n * g.C + c], cnt);
+                    if (sum) atomicAdd(&st.sumsq[rep_off + sp.n * g.C + c], sum);
+                    if (HAS_LABEL) s_lab[c] = 0u;
+                }
+            }
+        } else {
+            // MaxSquare: hand the running sum over when the next segment belongs to another image
+            const int next_n = (u < u_end) ? (int)((u / (unsigned)g.H) / TX) : -1;
+            if (next_n != sp.n) {
+                ms_acc = warp_sum_u64(ms_acc);
+                if (lane == 0 && ms_acc) atomicAdd(&st.sumsq[rep_off + sp.n * g.C], ms_acc);
+                ms_acc = 0ull;
+            }
+        }
     }
-    __syncthreads();
-    if (tid < g.C) {
-        if (s_hist[tid]) atomicAdd(&st.hist[sp.n * g.C + tid], s_hist[tid]);
-        if (s_sum[tid]) atomicAdd(&st.sumsq[sp.n * g.C + tid], s_sum[tid]);
-    }
-    if (tid == 0 && s_flags) atomicOr(st.flags, s_flags);
-    if (take_ticket_is_last(st.ticket, gridDim.x * gridDim.y * gridDim.z))
-        finalize_loss(st, IW ? MSQ_MODE_IW : MSQ_MODE_MAXSQUARE, n_img, g.C, r32, omr32, n_norm,
-                      (unsigned long long)n_img * g.C * g.H * g.W);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(st.flags, kFlagNonFinite);
 }
 
 // ------------------------------------------------------------------ K2: backward
 // dL/dz_c = a * p_c * (p_c - q),  a = -2 w[n,k] go / (Nn C)  (IW)   or   -go / (Nn C H W)  (MaxSquare)
-template <int CT, bool IW>
-__global__ void __launch_bounds__(kTW, 4)
-fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, int n_norm, const float* __restrict__ weights,
-                 const float* __restrict__ grad_out, float* __restrict__ grad_lo) {
-    extern __shared__ float s_dyn[];
-    float* s_tile = s_dyn;                                   // [C][nrm][ncp]
+template <int CT, bool PAD, bool IW>
+__global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
+fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
+                 const float* __restrict__ weights, const float* __restrict__ grad_out, float* __restrict__ grad_lo) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float* s_tile = (float*)s_raw;                           // [C][nrm][ncp]
     float* s_stage = s_tile + g.C * g.nrm * g.ncp;           // [C][kTW+1]
     float* s_lx0 = s_stage + g.C * (kTW + 1);                // [kTW]
     float* s_lx1 = s_lx0 + kTW;                              // [kTW]
@@ -275,186 +371,235 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, int n_norm
     int* s_rng = s_j1 + kTW;                                 // [4][ncp]: start0,end0,start1,end1
     __shared__ float s_coef[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x;
-    const Strip sp = make_strip(g);
     const float go = *grad_out;
-    if (IW && tid < g.C)
-        s_coef[tid] = (float)(-2.0 * (double)weights[sp.n * g.C + tid] * (double)go / ((double)n_norm * (double)g.C));
     const float coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
-    load_tile(s_tile, lo, g, sp);
+    const int Cd = PAD ? g.C : CT;                           // exact instantiations: constant divisor
 
-    const bool active = (sp.xs + tid) < sp.xe;
-    const int x = active ? sp.xs + tid : sp.xe - 1;
-    int x0, x1;
-    float lx0, lx1;
-    src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
-    const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
-    s_lx0[tid] = lx0;
-    s_lx1[tid] = lx1;
-    s_j0[tid] = active ? j0 : -1;
-    s_j1[tid] = active ? j1 : -1;
-    for (int i = tid; i < 4 * g.ncp; i += kTW) s_rng[i] = 0;
-    __syncthreads();
-    if (active) {
-        const bool last = (sp.xs + tid + 1 == sp.xe);
-        if (tid == 0 || s_j0[tid - 1] != j0) s_rng[0 * g.ncp + j0] = tid;
-        if (last || s_j0[tid + 1] != j0) s_rng[1 * g.ncp + j0] = tid + 1;
-        if (tid == 0 || s_j1[tid - 1] != j1) s_rng[2 * g.ncp + j1] = tid;
-        if (last || s_j1[tid + 1] != j1) s_rng[3 * g.ncp + j1] = tid + 1;
-    }
-    __syncthreads();
+    // units < 2^31 (checked on the host): 32-bit divisions only
+    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
+    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
+    int coef_img = -1;
+    while (u < u_end) {
+        const unsigned col = u / (unsigned)g.H;
+        const int ys = (int)(u - col * (unsigned)g.H);
+        const int ye = (int)min((unsigned)g.H, (unsigned)ys + (u_end - u));
+        u += (unsigned)(ye - ys);
+        const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
+        __syncthreads();                                     // previous segment done with all shared arrays
+        if (IW && sp.n != coef_img) {
+            if (tid < g.C)
+                s_coef[tid] = (float)(-2.0 * (double)weights[sp.n * g.C + tid] * (double)go /
+                                      ((double)n_norm * (double)g.C));
+            coef_img = sp.n;
+        }
+        load_tile(s_tile, lo, g, sp);
 
-    float Ha[CT], Hb[CT], dHa[CT], dHb[CT];
-    int ra = -1, rb = -1;
-
-    // horizontal adjoint of one finished low-res row: every thread parks its d t_r[c] in
-    // shared memory, then one thread per (class, low-res column) gathers its <=2 runs
-    // of output columns and issues one red.global.add.
-    auto flush_row = [&](int r, const float (&dH)[CT]) {
-#pragma unroll
-        for (int c = 0; c < CT; ++c)
-            if (c < g.C) s_stage[c * (kTW + 1) + tid] = active ? dH[c] : 0.f;
+        const bool active = (sp.xs + tid) < sp.xe;
+        const int x = active ? sp.xs + tid : sp.xe - 1;
+        int x0, x1;
+        float lx0, lx1;
+        src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
+        const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
+        s_lx0[tid] = lx0;
+        s_lx1[tid] = lx1;
+        s_j0[tid] = active ? j0 : -1;
+        s_j1[tid] = active ? j1 : -1;
+        for (int i = tid; i < 4 * g.ncp; i += kTW) s_rng[i] = 0;
         __syncthreads();
-        float* out = grad_lo + (((long long)sp.n * g.C) * g.h + r) * g.w + sp.c_lo;
-        const int Cd = (CT == 13 || CT == 16 || CT == 19) ? CT : g.C;   // exact instantiations: constant divisor
-        const int cells = Cd * sp.nc;
-        for (int idx = tid; idx < cells; idx += kTW) {
-            const int j = idx / Cd, c = idx - j * Cd;
-            const float* col = s_stage + c * (kTW + 1);
-            float acc = 0.f;
-            for (int t = s_rng[j], te = s_rng[g.ncp + j]; t < te; ++t) acc = fmaf(s_lx0[t], col[t], acc);
-            for (int t = s_rng[2 * g.ncp + j], te = s_rng[3 * g.ncp + j]; t < te; ++t) acc = fmaf(s_lx1[t], col[t], acc);
-            atomicAdd(out + (long long)c * g.h * g.w + j, acc);
+        if (active) {
+            const bool last = (sp.xs + tid + 1 == sp.xe);
+            if (tid == 0 || s_j0[tid - 1] != j0) s_rng[0 * g.ncp + j0] = tid;
+            if (last || s_j0[tid + 1] != j0) s_rng[1 * g.ncp + j0] = tid + 1;
+            if (tid == 0 || s_j1[tid - 1] != j1) s_rng[2 * g.ncp + j1] = tid;
+            if (last || s_j1[tid + 1] != j1) s_rng[3 * g.ncp + j1] = tid + 1;
         }
         __syncthreads();
-    };
 
-    for (int y = sp.ys; y < sp.ye; ++y) {
-        int y0, y1;
-        float ly0, ly1;
-        src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
-        if (y0 != ra) {
-            if (ra >= 0) flush_row(ra, dHa);
-            if (y0 == rb) {
+        constexpr int CP = (CT + 1) / 2;
+        float2 Ha[CP], Hb[CP], dHa[CP], dHb[CP];
+        int ra = -1, rb = -1;
+
+        // horizontal adjoint of one finished low-res row: every thread parks its d t_r[c] in
+        // shared memory, then one thread per (class, low-res column) gathers its <=2 runs
+        // of output columns and issues one red.global.add.
+        auto flush_row = [&](int r, const float2 (&dH)[CP]) {
 #pragma unroll
-                for (int c = 0; c < CT; ++c) { Ha[c] = Hb[c]; dHa[c] = dHb[c]; }
-            } else {
+            for (int c = 0; c < CT; ++c)
+                if (!PAD || c < g.C) s_stage[c * (kTW + 1) + tid] = active ? lane_of(dH[c >> 1], c) : 0.f;
+            __syncthreads();
+            float* out = grad_lo + (((long long)sp.n * g.C) * g.h + r) * g.w + sp.c_lo;
+            const int cells = Cd * sp.nc;
+            for (int idx = tid; idx < cells; idx += kTW) {
+                const int j = idx / Cd, c = idx - j * Cd;
+                const float* colp = s_stage + c * (kTW + 1);
+                float acc = 0.f;
+                for (int t = s_rng[j], te = s_rng[g.ncp + j]; t < te; ++t) acc = fmaf(s_lx0[t], colp[t], acc);
+                for (int t = s_rng[2 * g.ncp + j], te = s_rng[3 * g.ncp + j]; t < te; ++t) acc = fmaf(s_lx1[t], colp[t], acc);
+                atomicAdd(out + (long long)c * g.h * g.w + j, acc);
+            }
+            __syncthreads();
+        };
+
+        for (int y = sp.ys; y < sp.ye; ++y) {
+            int y0, y1;
+            float ly0, ly1;
+            src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
+            if (y0 != ra) {
+                if (ra >= 0) flush_row(ra, dHa);
+                if (y0 == rb) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) { Ha[p] = Hb[p]; dHa[p] = dHb[p]; }
+                } else {
+                    if (rb >= 0) flush_row(rb, dHb);
+                    hline<CT, PAD>(Ha, s_tile, g, y0 - sp.r_lo, j0, j1, lx0, lx1);
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) dHa[p] = make_float2(0.f, 0.f);
+                }
+                ra = y0;
+                rb = -1;
+            }
+            if (y1 != rb) {
                 if (rb >= 0) flush_row(rb, dHb);
-                hline<CT>(Ha, s_tile, g, y0 - sp.r_lo, j0, j1, lx0, lx1);
+                if (y1 == ra) {
 #pragma unroll
-                for (int c = 0; c < CT; ++c) dHa[c] = 0.f;
+                    for (int p = 0; p < CP; ++p) Hb[p] = Ha[p];
+                } else {
+                    hline<CT, PAD>(Hb, s_tile, g, y1 - sp.r_lo, j0, j1, lx0, lx1);
+                }
+#pragma unroll
+                for (int p = 0; p < CP; ++p) dHb[p] = make_float2(0.f, 0.f);
+                rb = y1;
             }
-            ra = y0;
-            rb = -1;
-        }
-        if (y1 != rb) {
-            if (rb >= 0) flush_row(rb, dHb);
-            if (y1 == ra) {
+            float2 z[CP], e[CP];
+            {
+                const float2 w0 = splat(ly0), w1 = splat(ly1);
 #pragma unroll
-                for (int c = 0; c < CT; ++c) Hb[c] = Ha[c];
-            } else {
-                hline<CT>(Hb, s_tile, g, y1 - sp.r_lo, j0, j1, lx0, lx1);
+                for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
             }
+            float inv_s, q, qs;
+            const int k = pixel_stats<CT, IW>(z, e, inv_s, q, qs);
+            // g_c = a p_c (p_c - q) = (a / s^2) e_c (e_c - q s)
+            const float a = (IW ? s_coef[k] : coef_ms) * inv_s * inv_s;
+            const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nqs = splat(-qs);
 #pragma unroll
-            for (int c = 0; c < CT; ++c) dHb[c] = 0.f;
-            rb = y1;
+            for (int p = 0; p < CP; ++p) {
+                const float2 v = __fmul2_rn(e[p], __fadd2_rn(e[p], nqs));
+                dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+            }
         }
-        float z[CT], e[CT];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) z[c] = __fmaf_rn(Ha[c], ly0, __fmul_rn(Hb[c], ly1));
-        float inv_s, q;
-        const int k = pixel_stats<CT, IW>(z, e, inv_s, q);
-        const float a = IW ? s_coef[k] : coef_ms;
-        const float a0 = a * ly0, a1 = a * ly1;
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-            const float p = e[c] * inv_s;
-            const float gz = p * (p - q);
-            dHa[c] = fmaf(a0, gz, dHa[c]);
-            dHb[c] = fmaf(a1, gz, dHb[c]);
-        }
+        if (ra >= 0) flush_row(ra, dHa);
+        if (rb >= 0) flush_row(rb, dHb);
     }
-    if (ra >= 0) flush_row(ra, dHa);
-    if (rb >= 0) flush_row(rb, dHb);
 }
 
 // ------------------------------------------------------------------ host side
-int g_fused_rows = 0;      // tuning knob: 0 = choose automatically
+int g_fused_rows = 0;      // tuning knob: 0 = automatic (one balanced wave), R = about R rows per CTA
 
-static int make_geo(int C, int h, int w, int H, int W, int n, FusedGeo& g) {
-    if (H < h || W < w) return MSQ_E_GEOMETRY;
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
+    }
+    return n;
+}
+
+struct Plan {
+    FusedGeo g;
+    long long units;
+    int grid;
+};
+
+// geometry + grid for `ctas_per_sm` co-resident CTAs per SM
+static int make_plan(int C, int h, int w, int H, int W, int n, int ctas_per_sm, Plan& p) {
+    if (H < h || W < w || H > 65535) return MSQ_E_GEOMETRY;
+    FusedGeo& g = p.g;
     g.C = C; g.h = h; g.w = w; g.H = H; g.W = W;
     g.sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
     g.sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
     const int tiles_x = (W + kTW - 1) / kTW;
-    int R = g_fused_rows;
-    if (R <= 0) {
-        // ~6 CTAs per SM in flight, strips no shorter than 4 rows and no longer than 32
-        const long long target = 6LL * kSMs;
-        R = (int)(((long long)H * tiles_x * n) / target);
-        if (R < 4) R = 4;
-        if (R > 32) R = 32;
-    }
-    if (R > H) R = H;
-    g.R = R;
-    // exact tile extents with the kernel's own index arithmetic
-    int nrm = 1, ncp = 1, i0, i1, a0;
-    float l0, l1;
-    for (int ys = 0; ys < H; ys += R) {
-        const int ye = (ys + R < H) ? ys + R : H;
-        src_index(g.sy, ys, h, a0, i1, l0, l1);
-        src_index(g.sy, ye - 1, h, i0, i1, l0, l1);
-        if (i1 - a0 + 1 > nrm) nrm = i1 - a0 + 1;
-    }
-    for (int xs = 0; xs < W; xs += kTW) {
-        const int xe = (xs + kTW < W) ? xs + kTW : W;
-        src_index(g.sx, xs, w, a0, i1, l0, l1);
-        src_index(g.sx, xe - 1, w, i0, i1, l0, l1);
-        if (i1 - a0 + 1 > ncp) ncp = i1 - a0 + 1;
-    }
+    p.units = (long long)n * tiles_x * H;
+    if (p.units >= (1LL << 31)) return MSQ_E_GEOMETRY;
+    long long grid = (long long)sm_count() * ctas_per_sm;
+    if (g_fused_rows > 0) grid = (p.units + g_fused_rows - 1) / g_fused_rows;
+    else if (p.units / grid < 4) grid = p.units / 4;          // tiny problems: at least 4 rows per CTA
+    if (grid < 1) grid = 1;
+    if (grid > p.units) grid = p.units;
+    p.grid = (int)grid;
+    long long rmax = (p.units + grid - 1) / grid;
+    if (rmax > H) rmax = H;
+    g.R = (int)rmax;
+    int nrm = (int)ceilf(g.sy * (float)(rmax - 1)) + 3;
+    int ncp = (int)ceilf(g.sx * (float)(kTW - 1)) + 3;
+    if (nrm > h) nrm = h;
+    if (ncp > w) ncp = w;
     g.nrm = nrm;
     g.ncp = ncp | 1;       // odd pitch: consecutive tile rows start in different banks
     return 0;
 }
 
-static dim3 fused_grid(const FusedGeo& g, int n) {
-    return dim3((unsigned)((g.W + kTW - 1) / kTW), (unsigned)((g.H + g.R - 1) / g.R), (unsigned)n);
+template <typename K>
+static int occupancy(K kernel, size_t smem, int fallback) {
+    int occ = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTW, smem) != cudaSuccess || occ < 1) occ = fallback;
+    return occ;
 }
 
-template <int CT>
-static int launch_fused_fwd(int mode, const float* lo, const FusedGeo& g, int n, const int64_t* label, float r32,
-                            float omr32, int nn, State st, cudaStream_t s) {
-    const size_t smem = (size_t)g.C * g.nrm * g.ncp * sizeof(float);
-    if (smem > 200 * 1024) return MSQ_E_SMEM;
-    const dim3 grid = fused_grid(g, n);
-#define MSQ_LAUNCH(K)                                                                             \
-    do {                                                                                          \
+static size_t fwd_smem(const FusedGeo& g, bool iw) {
+    return (iw ? (size_t)g.C * kTW * 8 : 0) + (size_t)g.C * g.nrm * g.ncp * sizeof(float);
+}
+static size_t bwd_smem(const FusedGeo& g) {
+    return ((size_t)g.C * g.nrm * g.ncp + (size_t)g.C * (kTW + 1) + 2 * kTW) * sizeof(float) +
+           (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int);
+}
+
+template <int CT, bool PAD>
+static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, const int64_t* label,
+                            float r32, float omr32, int nn, State st, cudaStream_t s) {
+    const bool iw = mode != MSQ_MODE_MAXSQUARE;
+#define MSQ_LAUNCH(K)                                                                          \
+    do {                                                                                       \
+        Plan p;                                                                                \
+        int rc = make_plan(C, h, w, H, W, n, MSQ_FWD_MINB, p);                                            \
+        if (rc) return rc;                                                                     \
+        const int occ = occupancy(K, fwd_smem(p.g, iw), 1);                                    \
+        if (occ != MSQ_FWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
+        const size_t smem = fwd_smem(p.g, iw);                                                 \
+        if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<grid, kTW, smem, s>>>(lo, g, n, label, r32, omr32, nn, st);                           \
+        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, label, st);                       \
     } while (0)
-    if (mode == MSQ_MODE_MAXSQUARE) MSQ_LAUNCH((fused_fwd_kernel<CT, false, false>));
-    else if (label) MSQ_LAUNCH((fused_fwd_kernel<CT, true, true>));
-    else MSQ_LAUNCH((fused_fwd_kernel<CT, true, false>));
+    if (!iw) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, false, false>));
+    else if (label) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, true>));
+    else MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, false>));
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
-    return 0;
+    return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s);
 }
 
-template <int CT>
-static int launch_fused_bwd(int mode, const float* lo, const FusedGeo& g, int n, int nn, State st,
+template <int CT, bool PAD>
+static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, int nn, State st,
                             const float* grad_out, float* grad_lo, cudaStream_t s) {
-    const size_t smem = ((size_t)g.C * g.nrm * g.ncp + (size_t)g.C * (kTW + 1) + 2 * kTW) * sizeof(float) +
-                        (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int);
-    if (smem > 200 * 1024) return MSQ_E_SMEM;
-    const dim3 grid = fused_grid(g, n);
-    cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * g.C * g.h * g.w * sizeof(float), s);
+    cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
     if (e != cudaSuccess) return (int)e;
-#define MSQ_LAUNCH(K)                                                                             \
-    do {                                                                                          \
+#define MSQ_LAUNCH(K)                                                                          \
+    do {                                                                                       \
+        Plan p;                                                                                \
+        int rc = make_plan(C, h, w, H, W, n, MSQ_BWD_MINB, p);                                            \
+        if (rc) return rc;                                                                     \
+        const int occ = occupancy(K, bwd_smem(p.g), 1);                                        \
+        if (occ != MSQ_BWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
+        const size_t smem = bwd_smem(p.g);                                                     \
+        if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<grid, kTW, smem, s>>>(lo, g, n, nn, st.weights, grad_out, grad_lo);                   \
+        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, nn, st.weights, grad_out, grad_lo);   \
     } while (0)
-    if (mode == MSQ_MODE_MAXSQUARE) MSQ_LAUNCH((fused_bwd_kernel<CT, false>));
-    else MSQ_LAUNCH((fused_bwd_kernel<CT, true>));
+    if (mode == MSQ_MODE_MAXSQUARE) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false>));
+    else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, true>));
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
     return 0;
@@ -466,13 +611,13 @@ using namespace msq;
 
 #define MSQ_DISPATCH_C(C, CALL)                  \
     switch (C) {                                 \
-        case 13: return CALL(13);                \
-        case 16: return CALL(16);                \
-        case 19: return CALL(19);                \
+        case 13: return CALL(13, false);         \
+        case 16: return CALL(16, false);         \
+        case 19: return CALL(19, false);         \
         default:                                 \
-            if ((C) <= 8) return CALL(8);        \
-            if ((C) <= 24) return CALL(24);      \
-            return CALL(32);                     \
+            if ((C) <= 8) return CALL(8, true);  \
+            if ((C) <= 24) return CALL(24, true);\
+            return CALL(32, true);               \
     }
 
 extern "C" int msq_fused_fwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
@@ -483,14 +628,11 @@ extern "C" int msq_fused_fwd(int mode, const float* logits, int n, int num_class
         return MSQ_E_BADARG;
     if (mode != MSQ_MODE_IW && mode != MSQ_MODE_MAXSQUARE) return MSQ_E_BADARG;
     if ((((uintptr_t)logits) & 3u) || ((((uintptr_t)accum) | ((uintptr_t)out)) & 15u) || (label && (((uintptr_t)label) & 7u))) return MSQ_E_ALIGN;
-    FusedGeo g;
-    const int rc = make_geo(num_class, h, w, out_h, out_w, n, g);
-    if (rc) return rc;
     const State st = carve(accum, out, n, num_class);
     const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
     cudaStream_t s = (cudaStream_t)stream;
-#define CALL(CT) launch_fused_fwd<CT>(mode, logits, g, n, label, r32, omr32, nn, st, s)
+#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, s)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
@@ -503,13 +645,10 @@ extern "C" int msq_fused_bwd(int mode, const float* logits, int n, int num_class
         return MSQ_E_BADARG;
     if (mode != MSQ_MODE_IW && mode != MSQ_MODE_MAXSQUARE) return MSQ_E_BADARG;
     if ((((uintptr_t)logits) | ((uintptr_t)grad_logits) | ((uintptr_t)grad_out)) & 3u) return MSQ_E_ALIGN;
-    FusedGeo g;
-    const int rc = make_geo(num_class, h, w, out_h, out_w, n, g);
-    if (rc) return rc;
     const State st = carve(nullptr, const_cast<void*>(out), n, num_class);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
     cudaStream_t s = (cudaStream_t)stream;
-#define CALL(CT) launch_fused_bwd<CT>(mode, logits, g, n, nn, st, grad_out, grad_logits, s)
+#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_logits, s)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }

@@ -19,44 +19,48 @@ __device__ __forceinline__ void max_step(float v, int c, float& best, int& arg) 
     if (v > best || (v != v && best == best)) { best = v; arg = c; }
 }
 
-struct PxAcc {            // run-length accumulator over the pixels one thread visits
-    int k;
-    unsigned cnt;
-    float q;
-};
-
-__device__ __forceinline__ void flush_run(PxAcc& r, unsigned* s_hist, unsigned long long* s_sum, unsigned* s_flags,
-                                          bool count_hist) {
-    if (r.k >= 0 && r.cnt) {
-        if (count_hist) atomicAdd(&s_hist[r.k], r.cnt);
-        if (!(fabsf(r.q) < 3.0e38f)) atomicOr(s_flags, kFlagNonFinite);
-        atomicAdd(&s_sum[r.k], to_fix(r.q));
-    }
-}
+constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
 
 // ------------------------------------------------------------------ K3: forward
-// grid (bx, N).  IW: hist/S per class.  MaxSquare: everything goes to bucket 0 and
-// `kept` counts the elements != ignore (utils/loss.py:117).
+// grid (bx, N).
+// IW: every thread owns, per class, a private packed accumulator in shared memory
+//     (pixel count << 48 | sum of q in 2^-32 fixed point).  A run of equal argmax
+//     classes costs one conflict-free LDS.64/STS.64 pair -- no shared atomics (64-bit
+//     shared atomics are CAS loops on this chip) and no dependence on how coherent the
+//     input is.  The CTA reduces its buckets with warp shuffles and issues one global
+//     atomic per class and warp.
+// MaxSquare: one bucket; q and the count of elements != ignore (utils/loss.py:117) are
+//     accumulated in registers, exactly (every 4-pixel sum is converted to fixed point).
 template <int CT, bool IW, bool HAS_LABEL, bool VEC>
 __global__ void __launch_bounds__(kProbThreads, CT > 0 ? 2 : 4)
 prob_fwd_kernel(const float* __restrict__ prob, int n_img, int C, long long hw, const int64_t* __restrict__ label,
-                float ignore_val, float r32, float omr32, int n_norm, State st) {
-    __shared__ unsigned s_hist[MSQ_MAX_CLASSES];
-    __shared__ unsigned long long s_sum[MSQ_MAX_CLASSES];
-    __shared__ unsigned long long s_kept;
-    __shared__ unsigned s_flags;
-    const int tid = threadIdx.x;
-    if (tid < MSQ_MAX_CLASSES) { s_hist[tid] = 0u; s_sum[tid] = 0ull; }
-    if (tid == 0) { s_kept = 0ull; s_flags = 0u; }
-    __syncthreads();
+                float ignore_val, State st) {
+    extern __shared__ __align__(16) unsigned long long s_bkt[];      // [C][kProbThreads]  (IW only)
+    __shared__ unsigned s_lab[MSQ_MAX_CLASSES];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (IW) {
+        for (int c = 0; c < C; ++c) s_bkt[c * kProbThreads + tid] = 0ull;
+        if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
+        if (HAS_LABEL) __syncthreads();
+    }
 
     const int n = blockIdx.y;
+    const int rep_off = (int)(blockIdx.x % kRep) * n_img * C;        // this CTA's accumulator replica
     const float* p_n = prob + (long long)n * C * hw;
     const int64_t* lab_n = HAS_LABEL ? label + (long long)n * hw : nullptr;
     constexpr int PX = VEC ? 4 : 1;
     const long long ngroups = (hw + PX - 1) / PX;
-    PxAcc run{-1, 0u, 0.f};
-    unsigned long long kept = 0ull;
+    int run_k = -1;
+    unsigned run_cnt = 0u;
+    float run_q = 0.f;
+    unsigned long long ms_sum = 0ull, kept = 0ull;
+    bool bad = false;
+    auto flush = [&]() {
+        if (run_k >= 0 && run_cnt) {
+            bad |= !(fabsf(run_q) < 3.0e38f);
+            s_bkt[run_k * kProbThreads + tid] += to_fix(run_q) + (HAS_LABEL ? 0ull : ((unsigned long long)run_cnt << 48));
+        }
+    };
 
     for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < ngroups; i += (long long)gridDim.x * blockDim.x) {
         const long long px = i * PX;
@@ -102,35 +106,48 @@ prob_fwd_kernel(const float* __restrict__ prob, int n_img, int C, long long hw, 
                 const int k = (best[j] != ignore_val) ? arg[j] : -1;
                 if (HAS_LABEL) {                                      // utils/loss.py:87-94: count `label`
                     const long long lv = lab_n[px + j];
-                    if (lv >= 0 && lv < C) atomicAdd(&s_hist[(int)lv], 1u);
+                    if (lv >= 0 && lv < C) atomicAdd(&s_lab[(int)lv], 1u);
                 }
-                if (k == run.k) { run.cnt++; run.q += q[j]; }
-                else { flush_run(run, s_hist, s_sum, &s_flags, !HAS_LABEL); run.k = k; run.cnt = 1u; run.q = q[j]; }
+                if (k == run_k) { run_cnt++; run_q += q[j]; }
+                else { flush(); run_k = k; run_cnt = 1u; run_q = q[j]; }
             }
         } else {
             float qs = 0.f;
 #pragma unroll
             for (int j = 0; j < PX; ++j) { qs += q[j]; kept += kcnt[j]; }
-            run.k = 0; run.cnt += PX; run.q += qs;
-            if (run.cnt >= 64u) { flush_run(run, s_hist, s_sum, &s_flags, false); run.cnt = 0u; run.q = 0.f; }
+            bad |= !(fabsf(qs) < 3.0e38f);
+            ms_sum += to_fix(qs);
         }
     }
-    flush_run(run, s_hist, s_sum, &s_flags, IW && !HAS_LABEL);
-    if (!IW) {
+    if (IW) {
+        flush();
+        __syncthreads();
+        for (int c = wid; c < C; c += kProbThreads / 32) {
+            unsigned cnt = 0u;
+            unsigned long long sum = 0ull;
+#pragma unroll
+            for (int t = 0; t < kProbThreads / 32; ++t) {
+                const unsigned long long v = s_bkt[c * kProbThreads + t * 32 + lane];
+                cnt += (unsigned)(v >> 48);
+                sum += v & kBktMask;
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            sum = warp_sum_u64(sum);
+            if (lane == 0) {
+                if (HAS_LABEL) cnt = s_lab[c];
+                if (cnt) atomicAdd(&st.hist[rep_off + n * C + c], cnt);
+                if (sum) atomicAdd(&st.sumsq[rep_off + n * C + c], sum);
+            }
+        }
+    } else {
+        ms_sum = warp_sum_u64(ms_sum);
         kept = warp_sum_u64(kept);
-        if ((tid & 31) == 0 && kept) atomicAdd(&s_kept, kept);
+        if (lane == 0) {
+            if (ms_sum) atomicAdd(&st.sumsq[rep_off + n * C], ms_sum);
+            if (kept) atomicAdd(st.kept, kept);
+        }
     }
-    __syncthreads();
-    if (tid < C) {
-        if (s_hist[tid]) atomicAdd(&st.hist[n * C + tid], s_hist[tid]);
-        if (s_sum[tid]) atomicAdd(&st.sumsq[n * C + tid], s_sum[tid]);
-    }
-    if (tid == 0) {
-        if (s_kept) atomicAdd(st.kept, s_kept);
-        if (s_flags) atomicOr(st.flags, s_flags);
-    }
-    if (take_ticket_is_last(st.ticket, gridDim.x * gridDim.y))
-        finalize_loss(st, IW ? MSQ_MODE_IW : MSQ_MODE_MAXSQUARE, n_img, C, r32, omr32, n_norm, 0ull);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(st.flags, kFlagNonFinite);
 }
 
 // ------------------------------------------------------------------ K4: backward
@@ -222,6 +239,8 @@ static dim3 stream_grid(long long hw, int n, int px, int ctas_per_sm) {
     long long bx = (groups + kProbThreads - 1) / kProbThreads;
     const long long cap = ((long long)kSMs * ctas_per_sm * 4 + n - 1) / n;    // ~4 waves over all images
     if (bx > cap) bx = cap;
+    const long long need = (groups + (long long)kProbThreads * 8192 - 1) / ((long long)kProbThreads * 8192);
+    if (bx < need) bx = need;          // packed 16-bit per-thread pixel counts: <= 8192 groups per thread
     if (bx < 1) bx = 1;
     return dim3((unsigned)bx, (unsigned)n);
 }
@@ -230,15 +249,18 @@ template <int CT, bool IW, bool HAS_LABEL>
 static int launch_fwd(const float* prob, int n, int C, long long hw, const int64_t* label, float ign, float r32,
                       float omr32, int n_norm, State st, cudaStream_t s) {
     const bool vec = ((hw & 3) == 0) && aligned16(prob);
+    const size_t smem = IW ? (size_t)C * kProbThreads * sizeof(unsigned long long) : 0;
     if (vec) {
-        prob_fwd_kernel<CT, IW, HAS_LABEL, true><<<stream_grid(hw, n, 4, CT > 0 ? 2 : 4), kProbThreads, 0, s>>>(
-            prob, n, C, hw, label, ign, r32, omr32, n_norm, st);
+        auto k = prob_fwd_kernel<CT, IW, HAS_LABEL, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<stream_grid(hw, n, 4, CT > 0 ? 2 : 4), kProbThreads, smem, s>>>(prob, n, C, hw, label, ign, st);
     } else {
-        prob_fwd_kernel<0, IW, HAS_LABEL, false><<<stream_grid(hw, n, 1, 4), kProbThreads, 0, s>>>(
-            prob, n, C, hw, label, ign, r32, omr32, n_norm, st);
+        auto k = prob_fwd_kernel<0, IW, HAS_LABEL, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<stream_grid(hw, n, 1, 4), kProbThreads, smem, s>>>(prob, n, C, hw, label, ign, st);
     }
     MSQ_CHECK_LAUNCH();
-    return 0;
+    return launch_finalize(st, IW ? MSQ_MODE_IW : MSQ_MODE_MAXSQUARE, n, C, r32, omr32, n_norm, 0ull, s);
 }
 
 template <int CT, bool IW>
