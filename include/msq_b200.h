@@ -150,8 +150,28 @@ int msq_confusion_i64(const int64_t* gt, const int64_t* pred, int64_t npix, int 
 int msq_confusion_logits_f32(const int64_t* gt, const float* logits, int n, int num_class,
                              int64_t hw, unsigned long long* cm, msq_stream_t stream);
 
-/* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "fused_rows" R; 0 =
- * automatic).  Results never depend on them. */
+/* ---------------------------------------------------------------------------
+ * Host-buffer pipeline (the one part of the library that owns memory): the fused
+ * step for callers whose tensors live in HOST memory.  Each submission copies the
+ * head logits H2D, runs msq_fused_fwd (+ msq_fused_bwd when host_grad != NULL) and
+ * copies loss / histogram / dL/dlogits back, on one of `depth` internal streams,
+ * so the copies of one step overlap the kernels of another.  The sequence mirrors
+ * tools/solve_gta5.py:366-371,199,217 (x.to(device) ... loss ... backward ...
+ * .item()).  Pin the host buffers for the copies to be asynchronous.
+ *   grad_scale  the upstream gradient (lambda_target), passed by value
+ *   slot_out    slot to hand to msq_pipe_wait before reading outputs / reusing inputs
+ * ------------------------------------------------------------------------- */
+typedef struct msq_pipe msq_pipe;
+int  msq_pipe_create(int mode, int n, int num_class, int h, int w, int out_h, int out_w,
+                     double ratio, int depth, msq_pipe** out);
+int  msq_pipe_submit(msq_pipe* pipe, const float* host_logits, float grad_scale, float* host_loss,
+                     float* host_grad /* nullable */, int32_t* host_hist /* nullable */, int* slot_out);
+int  msq_pipe_wait(msq_pipe* pipe, int slot);
+int  msq_pipe_drain(msq_pipe* pipe);
+void msq_pipe_destroy(msq_pipe* pipe);
+
+/* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "conf_ctas" 1|2,
+ * "prob_waves" W, "fused_rows" R; 0 = automatic).  Results never depend on them. */
 int msq_tune_set(const char* key, int value);
 
 #ifdef __cplusplus

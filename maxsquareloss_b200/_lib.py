@@ -16,7 +16,8 @@ MODE_IW = 1
 
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
-           "msq_fused_fwd", "msq_fused_bwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set")
+           "msq_fused_fwd", "msq_fused_bwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set",
+           "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
 class StateLayout(ctypes.Structure):
@@ -41,6 +42,7 @@ def load():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m maxsquareloss_b200.build` "
                 "(nvcc, sm_100a).  maxsquareloss_b200 has no CPU or PyTorch fallback.")
+        import torch  # noqa: F401  (loads PyTorch's libcudart.so.12 first: the library shares that runtime)
         lib = ctypes.CDLL(LIB_PATH)
         c = ctypes
         vp, i32, i64, dbl = c.c_void_p, c.c_int, c.c_int64, c.c_double
@@ -64,6 +66,16 @@ def load():
         lib.msq_confusion_logits_f32.argtypes = [vp, vp, i32, i32, i64, vp, vp]
         lib.msq_tune_set.restype = i32
         lib.msq_tune_set.argtypes = [c.c_char_p, i32]
+        lib.msq_pipe_create.restype = i32
+        lib.msq_pipe_create.argtypes = [i32, i32, i32, i32, i32, i32, i32, dbl, i32, c.POINTER(vp)]
+        lib.msq_pipe_submit.restype = i32
+        lib.msq_pipe_submit.argtypes = [vp, vp, c.c_float, vp, vp, vp, c.POINTER(i32)]
+        lib.msq_pipe_wait.restype = i32
+        lib.msq_pipe_wait.argtypes = [vp, i32]
+        lib.msq_pipe_drain.restype = i32
+        lib.msq_pipe_drain.argtypes = [vp]
+        lib.msq_pipe_destroy.restype = None
+        lib.msq_pipe_destroy.argtypes = [vp]
         if lib.msq_abi_version() != 1:
             raise RuntimeError("libmsq_b200.so ABI version mismatch; rebuild it")
         _lib = lib

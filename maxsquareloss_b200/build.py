@@ -14,10 +14,13 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmsq_b200.so")
-SOURCES = ["api.cu", "confusion.cu", "prob_loss.cu", "fused_loss.cu"]
+SOURCES = ["api.cu", "confusion.cu", "prob_loss.cu", "fused_loss.cu", "host_pipe.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(PKG), "include", "msq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "--shared", "-Xcompiler", "-fPIC",
+              # share libcudart.so.12 with PyTorch: one runtime instance => one notion of the current
+              # device, so torch.cuda.set_device(local_rank) also governs this library's launches
+              "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _nvcc():

@@ -4,6 +4,8 @@
 
 namespace msq {
 extern int g_conf_agg;      // confusion.cu
+extern int g_conf_ctas_per_sm;
+extern int g_prob_waves;    // prob_loss.cu
 extern int g_fused_rows;    // fused_loss.cu
 }
 
@@ -102,10 +104,14 @@ extern "C" int msq_state_layout_get(int n_images, int num_class, msq_state_layou
 
 // Performance-tuning knobs (bench sweeps); results never depend on them.
 //   "conf_agg"   0|1|2  warp aggregation level of the confusion histogram
-//   "fused_rows" R      output rows per strip of the fused kernels (0 = automatic)
+//   "conf_ctas"  1|2    1024-thread CTAs per SM of the int64 confusion kernel
+//   "prob_waves" W      grid of the strict kernels = W x co-resident capacity
+//   "fused_rows" R      about R output rows per CTA in the fused kernels (0 = automatic: one balanced wave)
 extern "C" int msq_tune_set(const char* key, int value) {
     if (!key) return MSQ_E_BADARG;
     if (!strcmp(key, "conf_agg")) { msq::g_conf_agg = value; return 0; }
+    if (!strcmp(key, "conf_ctas")) { msq::g_conf_ctas_per_sm = value; return 0; }
+    if (!strcmp(key, "prob_waves")) { msq::g_prob_waves = value; return 0; }
     if (!strcmp(key, "fused_rows")) { msq::g_fused_rows = value; return 0; }
     return MSQ_E_BADARG;
 }

@@ -149,6 +149,13 @@ __device__ __forceinline__ float iw_weight(float hist, float total, float r32, f
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                     unsigned long long kept_dense, cudaStream_t stream);
 
+// fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
+int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                       const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, cudaStream_t s);
+int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                       int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
+                       float* grad_logits, cudaStream_t s);
+
 }  // namespace msq
 
 #define MSQ_CHECK_LAUNCH()                       \

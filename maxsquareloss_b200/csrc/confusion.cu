@@ -88,13 +88,21 @@ __device__ __forceinline__ void merge_to_global(const unsigned* s_cm, int nbins,
 }
 
 // ------------------------------------------------------------------ K5a: int64 gt + int64 pred
+// One fat CTA per SM (1024 threads): every CTA merges its C*C bins into the caller's matrix
+// with global atomics, and a few hundred CTAs finishing together queue ~10 ns deep per
+// CTA on each of those addresses -- so few CTAs, each with kConfSub sub-histograms
+// (one per 8 warps) to keep shared-memory atomic contention at the 256-thread level.
+constexpr int kConfBig = 1024;
+constexpr int kConfSub = 4;
+
 template <int AGG, bool VEC>
-__global__ void __launch_bounds__(kConfThreads)
+__global__ void __launch_bounds__(kConfBig, 1)
 confusion_i64_kernel(const int64_t* __restrict__ gt, const int64_t* __restrict__ pred, long long npix, int C,
                      unsigned long long* __restrict__ cm, unsigned* __restrict__ errs) {
-    extern __shared__ unsigned s_cm[];
+    extern __shared__ unsigned s_all[];
     const int nbins = C * C;
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_cm[b] = 0u;
+    for (int b = threadIdx.x; b < nbins * kConfSub; b += blockDim.x) s_all[b] = 0u;
+    unsigned* s_cm = s_all + (threadIdx.x >> 8) * nbins;       // this warp group's sub-histogram
     __syncthreads();
 
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,7 +140,12 @@ confusion_i64_kernel(const int64_t* __restrict__ gt, const int64_t* __restrict__
         }
     }
     __syncthreads();
-    merge_to_global(s_cm, nbins, cm);
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+        unsigned long long v = 0ull;
+#pragma unroll
+        for (int k = 0; k < kConfSub; ++k) v += s_all[k * nbins + b];
+        if (v) atomicAdd(&cm[b], v);
+    }
 }
 
 // ------------------------------------------------------------------ K5b: argmax(logits) fused
@@ -224,20 +237,21 @@ confusion_logits_kernel(const int64_t* __restrict__ gt, const float* __restrict_
     merge_to_global(s_cm, nbins, cm);
 }
 
-int g_conf_agg = 1;   // tuning knob (msq_tune_set), see api.cu
+int g_conf_ctas_per_sm = 1;   // tuning knob: 1024-thread CTAs per SM for the int64 kernel (1 or 2)
+int g_conf_agg = 0;   // tuning knob (msq_tune_set), see api.cu; 0 measured fastest on B200
 
 template <int AGG>
 static int launch_i64(const int64_t* gt, const int64_t* pred, long long npix, int C, unsigned long long* cm,
                       unsigned* errs, cudaStream_t st) {
     const bool vec = ((((uintptr_t)gt) | ((uintptr_t)pred)) & 15u) == 0;
     const long long groups = (npix + 3) / 4;
-    long long blocks = (groups + kConfThreads - 1) / kConfThreads;
-    const long long cap = (long long)kSMs * 8;               // 8 x 256 threads = full SM occupancy
+    long long blocks = (groups + kConfBig - 1) / kConfBig;
+    const long long cap = (long long)kSMs * (g_conf_ctas_per_sm > 0 ? g_conf_ctas_per_sm : 1);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const size_t smem = (size_t)C * C * sizeof(unsigned);
-    if (vec) confusion_i64_kernel<AGG, true><<<(unsigned)blocks, kConfThreads, smem, st>>>(gt, pred, npix, C, cm, errs);
-    else confusion_i64_kernel<AGG, false><<<(unsigned)blocks, kConfThreads, smem, st>>>(gt, pred, npix, C, cm, errs);
+    const size_t smem = (size_t)C * C * sizeof(unsigned) * kConfSub;
+    if (vec) confusion_i64_kernel<AGG, true><<<(unsigned)blocks, kConfBig, smem, st>>>(gt, pred, npix, C, cm, errs);
+    else confusion_i64_kernel<AGG, false><<<(unsigned)blocks, kConfBig, smem, st>>>(gt, pred, npix, C, cm, errs);
     MSQ_CHECK_LAUNCH();
     return 0;
 }

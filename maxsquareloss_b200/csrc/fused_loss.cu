@@ -360,7 +360,8 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
 template <int CT, bool PAD, bool IW>
 __global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
 fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
-                 const float* __restrict__ weights, const float* __restrict__ grad_out, float* __restrict__ grad_lo) {
+                 const float* __restrict__ weights, const float* __restrict__ grad_out, float grad_out_value,
+                 float* __restrict__ grad_lo) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float* s_tile = (float*)s_raw;                           // [C][nrm][ncp]
     float* s_stage = s_tile + g.C * g.nrm * g.ncp;           // [C][kTW+1]
@@ -371,7 +372,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     int* s_rng = s_j1 + kTW;                                 // [4][ncp]: start0,end0,start1,end1
     __shared__ float s_coef[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x;
-    const float go = *grad_out;
+    const float go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
     const float coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
     const int Cd = PAD ? g.C : CT;                           // exact instantiations: constant divisor
 
@@ -583,7 +584,7 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
 
 template <int CT, bool PAD>
 static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, int nn, State st,
-                            const float* grad_out, float* grad_lo, cudaStream_t s) {
+                            const float* grad_out, float grad_out_value, float* grad_lo, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
     if (e != cudaSuccess) return (int)e;
 #define MSQ_LAUNCH(K)                                                                          \
@@ -596,7 +597,7 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
         const size_t smem = bwd_smem(p.g);                                                     \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, nn, st.weights, grad_out, grad_lo);   \
+        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, nn, st.weights, grad_out, grad_out_value, grad_lo); \
     } while (0)
     if (mode == MSQ_MODE_MAXSQUARE) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false>));
     else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, true>));
@@ -606,8 +607,6 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
 }
 
 }  // namespace msq
-
-using namespace msq;
 
 #define MSQ_DISPATCH_C(C, CALL)                  \
     switch (C) {                                 \
@@ -620,9 +619,10 @@ using namespace msq;
             return CALL(32, true);               \
     }
 
-extern "C" int msq_fused_fwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
-                             const int64_t* label, double ratio, int n_images_norm, void* accum, void* out,
-                             msq_stream_t stream) {
+namespace msq {
+
+int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                       const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, cudaStream_t s) {
     if (!logits || !accum || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES || h < 1 || w < 1 || out_h < 1 ||
         out_w < 1)
         return MSQ_E_BADARG;
@@ -631,24 +631,39 @@ extern "C" int msq_fused_fwd(int mode, const float* logits, int n, int num_class
     const State st = carve(accum, out, n, num_class);
     const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-    cudaStream_t s = (cudaStream_t)stream;
 #define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, s)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
 
-extern "C" int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
-                             int n_images_norm, const void* out, const float* grad_out, float* grad_logits,
-                             msq_stream_t stream) {
-    if (!logits || !out || !grad_out || !grad_logits || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES ||
+int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                       int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
+                       float* grad_logits, cudaStream_t s) {
+    if (!logits || !out || !grad_logits || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES ||
         h < 1 || w < 1 || out_h < 1 || out_w < 1)
         return MSQ_E_BADARG;
     if (mode != MSQ_MODE_IW && mode != MSQ_MODE_MAXSQUARE) return MSQ_E_BADARG;
     if ((((uintptr_t)logits) | ((uintptr_t)grad_logits) | ((uintptr_t)grad_out)) & 3u) return MSQ_E_ALIGN;
     const State st = carve(nullptr, const_cast<void*>(out), n, num_class);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-    cudaStream_t s = (cudaStream_t)stream;
-#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_logits, s)
+#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, s)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
+}
+
+}  // namespace msq
+
+extern "C" int msq_fused_fwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                             const int64_t* label, double ratio, int n_images_norm, void* accum, void* out,
+                             msq_stream_t stream) {
+    return msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, label, ratio, n_images_norm, accum, out,
+                                   (cudaStream_t)stream);
+}
+
+extern "C" int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                             int n_images_norm, const void* out, const float* grad_out, float* grad_logits,
+                             msq_stream_t stream) {
+    if (!grad_out) return MSQ_E_BADARG;
+    return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, 0.f,
+                                   grad_logits, (cudaStream_t)stream);
 }

@@ -1,0 +1,130 @@
+// Host-buffer pipeline: the fused loss step (H2D of the head logits, forward, finalise,
+// backward, D2H of the loss / histogram / dL/dlogits) for callers whose tensors live in
+// HOST memory, with `depth` submissions in flight on separate streams so that the copies
+// of one step overlap the kernels of another.  This is the non-PyTorch way into the hot
+// path (tools/solve_gta5.py:366-371,199,217 do the same sequence with torch ops: x.to(device),
+// model head, loss, backward, .item()).
+#include <new>
+#include "common.cuh"
+
+using namespace msq;
+
+struct msq_pipe {
+    int mode, n, C, h, w, H, W, depth;
+    double ratio;
+    size_t lo_bytes;
+    msq_state_layout lay;
+    struct Slot {
+        cudaStream_t stream;
+        cudaEvent_t done;
+        float* d_logits;
+        float* d_grad;
+        unsigned char* d_accum;
+        unsigned char* d_out;
+        bool busy;
+    } * slots;
+    unsigned long long submitted;
+};
+
+static void pipe_free(msq_pipe* p) {
+    if (!p) return;
+    if (p->slots) {
+        for (int i = 0; i < p->depth; ++i) {
+            msq_pipe::Slot& s = p->slots[i];
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.d_logits) cudaFree(s.d_logits);
+            if (s.d_grad) cudaFree(s.d_grad);
+            if (s.d_accum) cudaFree(s.d_accum);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        delete[] p->slots;
+    }
+    delete p;
+}
+
+extern "C" int msq_pipe_create(int mode, int n, int num_class, int h, int w, int out_h, int out_w, double ratio,
+                               int depth, msq_pipe** out) {
+    if (!out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES || h < 1 || w < 1 || out_h < h || out_w < w ||
+        depth < 1 || depth > 16)
+        return MSQ_E_BADARG;
+    if (mode != MSQ_MODE_IW && mode != MSQ_MODE_MAXSQUARE) return MSQ_E_BADARG;
+    msq_pipe* p = new (std::nothrow) msq_pipe();
+    if (!p) return (int)cudaErrorMemoryAllocation;
+    p->mode = mode; p->n = n; p->C = num_class; p->h = h; p->w = w; p->H = out_h; p->W = out_w;
+    p->depth = depth; p->ratio = ratio; p->submitted = 0;
+    p->lo_bytes = (size_t)n * num_class * h * w * sizeof(float);
+    p->lay = make_layout(n, num_class);
+    p->slots = new (std::nothrow) msq_pipe::Slot[depth]();
+    if (!p->slots) { delete p; return (int)cudaErrorMemoryAllocation; }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+        msq_pipe::Slot& s = p->slots[i];
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&s.d_logits, p->lo_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&s.d_grad, p->lo_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&s.d_accum, (size_t)p->lay.accum_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&s.d_out, (size_t)p->lay.out_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s.d_accum, 0, (size_t)p->lay.accum_bytes, s.stream)) != cudaSuccess) break;
+    }
+    if (e != cudaSuccess) { pipe_free(p); return (int)e; }
+    *out = p;
+    return 0;
+}
+
+extern "C" int msq_pipe_wait(msq_pipe* p, int slot) {
+    if (!p || slot < 0 || slot >= p->depth) return MSQ_E_BADARG;
+    msq_pipe::Slot& s = p->slots[slot];
+    if (!s.busy) return 0;
+    const cudaError_t e = cudaEventSynchronize(s.done);
+    s.busy = false;
+    return (int)e;
+}
+
+// Enqueue one step.  Host buffers should be pinned (cudaHostAlloc / torch pin_memory) for the
+// copies to be asynchronous; host_grad / host_hist may be NULL (no backward / no histogram).
+// Returns in *slot_out the slot to pass to msq_pipe_wait before reading the outputs or
+// reusing the input buffer.  If the slot is still busy the call first waits for it.
+extern "C" int msq_pipe_submit(msq_pipe* p, const float* host_logits, float grad_scale, float* host_loss,
+                               float* host_grad, int32_t* host_hist, int* slot_out) {
+    if (!p || !host_logits || !host_loss) return MSQ_E_BADARG;
+    const int slot = (int)(p->submitted % (unsigned long long)p->depth);
+    msq_pipe::Slot& s = p->slots[slot];
+    int rc = msq_pipe_wait(p, slot);
+    if (rc) return rc;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(s.d_logits, host_logits, p->lo_bytes, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) return (int)e;
+    rc = fused_fwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, nullptr, p->ratio, 0, s.d_accum,
+                            s.d_out, s.stream);
+    if (rc) return rc;
+    if (host_grad) {
+        rc = fused_bwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, 0, s.d_out, nullptr, grad_scale,
+                                s.d_grad, s.stream);
+        if (rc) return rc;
+        if ((e = cudaMemcpyAsync(host_grad, s.d_grad, p->lo_bytes, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return (int)e;
+    }
+    if ((e = cudaMemcpyAsync(host_loss, s.d_out + p->lay.loss_off, sizeof(float), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return (int)e;
+    if (host_hist) {
+        e = cudaMemcpyAsync(host_hist, s.d_out + p->lay.hist_out_off, (size_t)p->n * p->C * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) return (int)e;
+    s.busy = true;
+    p->submitted++;
+    if (slot_out) *slot_out = slot;
+    return 0;
+}
+
+extern "C" int msq_pipe_drain(msq_pipe* p) {
+    if (!p) return MSQ_E_BADARG;
+    for (int i = 0; i < p->depth; ++i) {
+        const int rc = msq_pipe_wait(p, i);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" void msq_pipe_destroy(msq_pipe* p) { pipe_free(p); }

@@ -234,10 +234,14 @@ prob_bwd_kernel(const float* __restrict__ prob, int C, long long hw, float ignor
 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
+int g_prob_waves = 1;     // tuning knob: grid = waves x (SMs x CTAs/SM), split over the images
+
 static dim3 stream_grid(long long hw, int n, int px, int ctas_per_sm) {
+    // persistent grid-stride CTAs: exactly `waves` x the co-resident capacity, so the per-CTA
+    // epilogue (bucket reduction, global atomics) is amortised over many pixel groups
     const long long groups = (hw + px - 1) / px;
     long long bx = (groups + kProbThreads - 1) / kProbThreads;
-    const long long cap = ((long long)kSMs * ctas_per_sm * 4 + n - 1) / n;    // ~4 waves over all images
+    const long long cap = ((long long)kSMs * ctas_per_sm * (g_prob_waves > 0 ? g_prob_waves : 1) + n - 1) / n;
     if (bx > cap) bx = cap;
     const long long need = (groups + (long long)kProbThreads * 8192 - 1) / ((long long)kProbThreads * 8192);
     if (bx < need) bx = need;          // packed 16-bit per-thread pixel counts: <= 8192 groups per thread

@@ -82,7 +82,7 @@ prob = torch.softmax(torch.nn.functional.interpolate(lo, size=HW, mode="bilinear
 go = torch.ones((), device=dev)
 for kind in ("iw", "ms"):
     crit = msq.IW_MaxSquareloss(-1, C, 0.2) if kind == "iw" else msq.MaxSquareloss(-1, C)
-    for R in (0, 4, 8, 16, 32):
+    for R in (0,):
         _lib.tune("fused_rows", R)
         x = lo.clone().requires_grad_(True)
         def fwd(): return crit(x, out_size=HW)
@@ -92,28 +92,46 @@ for kind in ("iw", "ms"):
         tf = t_ms(fwd); tfb = t_ms(fb)
         print(f"fused {kind} R={R}: fwd {tf*1e3:.1f} us  fwd+bwd {tfb*1e3:.1f} us  -> {npx/tfb/1e6:.2f} Gpix/s")
     _lib.tune("fused_rows", 0)
-    pg = prob.clone().requires_grad_(True)
-    def sf(): return crit(None, pg)
-    def sfb():
-        pg.grad = None
-        crit(None, pg).backward()
-    tf = t_ms(sf); tfb = t_ms(sfb)
-    bytes_f = 4 * C * npx; bytes_fb = 12 * C * npx
-    print(f"strict {kind}: fwd {tf*1e3:.1f} us ({bytes_f/tf/1e6:.0f} GB/s)  fwd+bwd {tfb*1e3:.1f} us ({bytes_fb/tfb/1e6:.0f} GB/s) -> {npx/tfb/1e6:.2f} Gpix/s")
+    probs = [prob, prob.clone()]
+    gradb = [torch.empty_like(prob), torch.empty_like(prob)]
+    lay = _lib.state_layout(N, C)
+    accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev); outb = torch.empty(lay.out_bytes, dtype=torch.uint8, device=dev)
+    lib = _lib.load(); st = torch.cuda.current_stream().cuda_stream
+    mode = 1 if kind == "iw" else 0
+    kk = [0]
+    def sf():
+        j = kk[0] % 2; kk[0] += 1
+        lib.msq_prob_fwd(mode, probs[j].data_ptr(), N, C, HW[0] * HW[1], None, 0.2, -1, 0, accum.data_ptr(), outb.data_ptr(), st)
+    def sb():
+        j = kk[0] % 2; kk[0] += 1
+        lib.msq_prob_bwd(mode, probs[j].data_ptr(), N, C, HW[0] * HW[1], -1, 0, outb.data_ptr(), go.data_ptr(), gradb[j].data_ptr(), st)
+    tf = t_ms(sf, iters=50); tb = t_ms(sb, iters=50)
+    bytes_f = 4 * C * npx; bytes_b = 8 * C * npx
+    print(f"strict {kind}: fwd {tf*1e3:.1f} us ({bytes_f/tf/1e6:.0f} GB/s)  bwd {tb*1e3:.1f} us ({bytes_b/tb/1e6:.0f} GB/s) -> fwd+bwd {npx/(tf+tb)/1e6:.2f} Gpix/s")
 
-# eval timings: big buffers (> L2)
-for C, n, HWs in [(19, 16, (720, 1280)), (16, 32, (512, 1024))]:
-    gt = synth.blocky_labels(n, HWs, C, 3).to(dev); pr = synth.noisy_prediction(gt.cpu(), C, 3).to(dev)
+# eval timings
+for C, n, HWs in [(19, 2, (720, 1280)), (19, 16, (720, 1280)), (16, 32, (512, 1024))]:
+    pool = max(1, int(200e6 // (16 * n * HWs[0] * HWs[1])))
+    gts = [synth.blocky_labels(n, HWs, C, 3 + i).to(dev) for i in range(pool)]
+    prs = [synth.noisy_prediction(g.cpu(), C, 3).to(dev) for g in gts]
     gtr = synth.random_labels(n, HWs, C, 4).to(dev); prr = torch.randint(0, C, gtr.shape, device=dev)
     ev = msq.Eval(C)
-    for agg in (0, 1, 2):
-        _lib.tune("conf_agg", agg)
-        for name, g_, p_ in (("blocky", gt, pr), ("uniform", gtr, prr)):
-            t = t_ms(lambda: ev.add_batch(g_, p_), iters=10, warm=3)
-            print(f"conf_i64 C{C} {name} agg{agg}: {t*1e3:.1f} us  {g_.numel()/t/1e6:.1f} Gpix/s  {16*g_.numel()/t/1e6:.0f} GB/s")
-    _lib.tune("conf_agg", 1)
-    lg = torch.randn(4, C, *HWs, device=dev)
-    g4 = gt[:4].contiguous()
-    t = t_ms(lambda: ev.add_batch_logits(g4, lg), iters=10, warm=3)
-    print(f"conf_logits C{C}: {t*1e3:.1f} us  {g4.numel()/t/1e6:.1f} Gpix/s  {(4*C+8)*g4.numel()/t/1e6:.0f} GB/s")
+    cmp = ev._dev.data_ptr()
+    lib = _lib.load(); st = torch.cuda.current_stream().cuda_stream
+    for ctas in (1, 2):
+        _lib.tune("conf_ctas", ctas)
+        for agg in (0, 1):
+            _lib.tune("conf_agg", agg)
+            for name, G, P in (("blocky", gts, prs), ("uniform", [gtr], [prr])):
+                k = [0]
+                def f():
+                    j = k[0] % len(G); k[0] += 1
+                    lib.msq_confusion_i64(G[j].data_ptr(), P[j].data_ptr(), G[j].numel(), C, cmp, cmp + 8 * C * C, st)
+                t = t_ms(f, iters=50, warm=5)
+                print(f"conf_i64 C{C} n{n} {name} ctas{ctas} agg{agg}: {t*1e3:.1f} us  {G[0].numel()/t/1e6:.1f} Gpix/s  {16*G[0].numel()/t/1e6:.0f} GB/s")
+    _lib.tune("conf_agg", 0); _lib.tune("conf_ctas", 1)
+    lg = torch.randn(min(n, 4), C, *HWs, device=dev)
+    g4 = gts[0][:min(n, 4)].contiguous()
+    t = t_ms(lambda: lib.msq_confusion_logits_f32(g4.data_ptr(), lg.data_ptr(), g4.shape[0], C, HWs[0] * HWs[1], cmp, st), iters=20, warm=3)
+    print(f"conf_logits C{C} n{g4.shape[0]}: {t*1e3:.1f} us  {g4.numel()/t/1e6:.1f} Gpix/s  {(4*C+8)*g4.numel()/t/1e6:.0f} GB/s")
 print("done")

@@ -271,3 +271,37 @@ def test_api_contract(msq):
         crit(None, prob.double())
     with pytest.raises(RuntimeError):
         crit(lo, out_size=(4, 4))                                    # downsampling is not supported
+
+
+def test_host_pipeline_matches_oracle(msq):
+    """C-ABI host-buffer pipeline (msq_pipe_*): pinned host logits in, loss / hist / dL/dlogits out."""
+    from oracle import loss_port
+    C, hw, HW = synth.SHAPES["tiny13"]
+    pipe = msq.HostPipeline("iw", 2, C, hw, HW, ratio=0.2, depth=2)
+    refs, outs = [], []
+    for seed in range(5):                     # more submissions than slots: slots are recycled
+        lo = synth.head_logits(2, C, hw, 50 + seed, 2.0)
+        refs.append(loss_port.chain_iw_maxsquare(lo, HW, C, 0.2, 0.1))
+        bufs = (lo.pin_memory(), torch.empty(()).pin_memory(), torch.empty_like(lo).pin_memory(),
+                torch.empty(2, C, dtype=torch.int32).pin_memory())
+        slot = pipe.submit(bufs[0], bufs[1], bufs[2], bufs[3], grad_scale=0.1)
+        outs.append((slot, bufs))
+        if seed >= 1:                          # read the previous submission while this one runs
+            pslot, pb = outs[seed - 1]
+            pipe.wait(pslot)
+            rl, rg, rh = refs[seed - 1]
+            assert abs(pb[1].item() - rl.item()) <= LOSS_RTOL * abs(rl.item())
+            assert pb[3].long().tolist() == rh.tolist()
+            _grad_close(pb[2], rg)
+    pipe.drain()
+    rl, rg, rh = refs[-1]
+    assert abs(outs[-1][1][1].item() - rl.item()) <= LOSS_RTOL * abs(rl.item())
+    _grad_close(outs[-1][1][2], rg)
+    pipe.close()
+    ms = msq.HostPipeline("maxsquare", 1, C, hw, HW)
+    lo = synth.head_logits(1, C, hw, 9, 2.0)
+    rl, rg = loss_port.chain_maxsquare(lo, HW, 1.0)
+    loss, grad = torch.empty(()).pin_memory(), torch.empty_like(lo).pin_memory()
+    ms.wait(ms.submit(lo.pin_memory(), loss, grad))
+    assert abs(loss.item() - rl.item()) <= LOSS_RTOL * abs(rl.item())
+    _grad_close(grad, rg)
