@@ -401,7 +401,7 @@ def run_b200(args, rank, world, local_rank):
         line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -465,6 +465,37 @@ def maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, acc_ptr, go_ptr, n_
     return {"metric": "MaxSquare fwd+bwd Gpixel/s", "value": PX_PER_STEP / t / 1e6, "ms_per_step": t}
 
 
+class _QuietStdout:
+    """Route everything written to fd 1 (e.g. NCCL's version banner) to stderr so that the only
+    thing on stdout is the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -483,7 +514,11 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
-    run_b200(args, rank, world, local_rank)
+    global _OUT
+    with _QuietStdout() as q:
+        _OUT = q
+        run_b200(args, rank, world, local_rank)
+    _OUT = None
 
 
 if __name__ == "__main__":
