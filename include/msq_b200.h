@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSQ_ABI_VERSION 1
+#define MSQ_ABI_VERSION 2
 #define MSQ_MAX_CLASSES 32          /* reference uses 13 / 16 / 19 */
 
 #define MSQ_E_BADARG   (-1)         /* null pointer, non-positive size, C > MSQ_MAX_CLASSES */
@@ -123,15 +123,27 @@ int msq_prob_bwd(int mode, const float* prob, int n, int num_class, int64_t hw,
  * full-resolution tensor is read or written.
  *   logits      float32 [N,C,h,w]
  *   label       int64 [N,H,W] or NULL (IW `label=` argument, full resolution)
+ *   aux         optional (NULL = off) per-pixel statistics cache of
+ *               msq_fused_aux_bytes(N,H,W) = 16*N*H*W bytes (float4 {max, q*s, 1/s^2,
+ *               argmax class}): written by the forward, and when handed to the
+ *               backward it skips re-deriving them (~55 % fewer instructions).  Not a
+ *               probability tensor: 16 B/pixel instead of 4*C.
+ *   zero_grad   optional float32 [N,C,h,w] buffer the forward zero-fills on the side
+ *               (pass the future grad_logits and grad_is_zeroed=1 to the backward to
+ *               save the memset launch)
  *   grad_logits float32 [N,C,h,w], overwritten
  * ------------------------------------------------------------------------- */
+int64_t msq_fused_aux_bytes(int n, int out_h, int out_w);
+
 int msq_fused_fwd(int mode, const float* logits, int n, int num_class, int h, int w,
                   int out_h, int out_w, const int64_t* label, double ratio,
-                  int n_images_norm, void* accum, void* out, msq_stream_t stream);
+                  int n_images_norm, void* accum, void* out, void* aux /* nullable */,
+                  float* zero_grad /* nullable */, msq_stream_t stream);
 
 int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, int w,
                   int out_h, int out_w, int n_images_norm, const void* out,
-                  const float* grad_out, float* grad_logits, msq_stream_t stream);
+                  const void* aux /* nullable */, const float* grad_out, float* grad_logits,
+                  int grad_is_zeroed, msq_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Evaluation: Eval.__generate_matrix / add_batch (utils/eval.py:109-121).

@@ -15,7 +15,7 @@ MODE_MAXSQUARE = 0
 MODE_IW = 1
 
 #: every symbol include/msq_b200.h declares
-SYMBOLS = ("msq_abi_version", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
+SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
            "msq_fused_fwd", "msq_fused_bwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set",
            "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
@@ -57,9 +57,11 @@ def load():
         lib.msq_prob_bwd.restype = i32
         lib.msq_prob_bwd.argtypes = [i32, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp]
         lib.msq_fused_fwd.restype = i32
-        lib.msq_fused_fwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, vp, dbl, i32, vp, vp, vp]
+        lib.msq_fused_fwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, vp, dbl, i32, vp, vp, vp, vp, vp]
         lib.msq_fused_bwd.restype = i32
-        lib.msq_fused_bwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.msq_fused_bwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+        lib.msq_fused_aux_bytes.restype = i64
+        lib.msq_fused_aux_bytes.argtypes = [i32, i32, i32]
         lib.msq_confusion_i64.restype = i32
         lib.msq_confusion_i64.argtypes = [vp, vp, i64, i32, vp, vp, vp]
         lib.msq_confusion_logits_f32.restype = i32
@@ -76,7 +78,7 @@ def load():
         lib.msq_pipe_drain.argtypes = [vp]
         lib.msq_pipe_destroy.restype = None
         lib.msq_pipe_destroy.argtypes = [vp]
-        if lib.msq_abi_version() != 1:
+        if lib.msq_abi_version() != 2:
             raise RuntimeError("libmsq_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

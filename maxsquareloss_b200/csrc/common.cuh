@@ -151,10 +151,11 @@ int launch_finalize(const State& st, int mode, int n, int C, float r32, float om
 
 // fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
-                       const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, cudaStream_t s);
+                       const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
+                       float* zero_grad, cudaStream_t s);
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
-                       float* grad_logits, cudaStream_t s);
+                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s);
 
 }  // namespace msq
 

@@ -92,20 +92,27 @@ __device__ __forceinline__ float lane_of(const float2& v, int c) { return (c & 1
 //   e[c] = 2^((z_c - m) log2 e), inv_s = 1/s with s = sum e, q = sum_c p_c^2, qs = q*s;
 //   returns the argmax class.
 template <int CT, bool NEED_ARG>
-__device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], float2 (&e)[(CT + 1) / 2], float& inv_s,
-                                           float& q, float& qs) {
+__device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], float2 (&e)[(CT + 1) / 2], float& m_out,
+                                           float& inv_s, float& q, float& qs) {
     constexpr int CP = (CT + 1) / 2;
     float m = z[0].x;
 #pragma unroll
     for (int c = 1; c < CT; ++c) m = fmaxf(m, lane_of(z[c >> 1], c));
+    m_out = m;
     int k = 0;
     if (NEED_ARG) {
         const float thr = m - kNearTie;
-        unsigned mask = 0u;
+        unsigned mask_a = 0u, mask_b = 0u;              // two chains: the ORs are serial per register
 #pragma unroll
-        for (int c = 0; c < CT; ++c)                    // one FSETP + one predicated LOP3 per class
-            asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
-                : "+r"(mask) : "f"(lane_of(z[c >> 1], c)), "f"(thr), "r"(1u << c));
+        for (int c = 0; c < CT; ++c) {                  // one FSETP + one predicated LOP3 per class
+            if (c & 1)
+                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(mask_b) : "f"(z[c >> 1].y), "f"(thr), "r"(1u << c));
+            else
+                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(mask_a) : "f"(z[c >> 1].x), "f"(thr), "r"(1u << c));
+        }
+        const unsigned mask = mask_a | mask_b;
         k = __ffs(mask) - 1;
         if (mask & (mask - 1u)) {                       // more than one class within 2^-22 of the max
             asm volatile("" ::: "memory");              // keep the spill of z[] inside this cold branch
@@ -117,20 +124,27 @@ __device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], floa
         if (k < 0) k = 0;                               // NaN logits: reference yields NaN loss anyway
     }
     const float2 l2e = splat(kLog2e), nm = splat(-m * kLog2e);
-    float2 s2 = make_float2(0.f, 0.f), ss2 = make_float2(0.f, 0.f);
+    float2 s2a = make_float2(0.f, 0.f), s2b = s2a, ss2a = s2a, ss2b = s2a;
 #pragma unroll
     for (int p = 0; p < CP; ++p) {
         const float2 t = __ffma2_rn(z[p], l2e, nm);
         e[p] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-        s2 = __fadd2_rn(s2, e[p]);
-        ss2 = __ffma2_rn(e[p], e[p], ss2);
+        if (p & 1) { s2b = __fadd2_rn(s2b, e[p]); ss2b = __ffma2_rn(e[p], e[p], ss2b); }
+        else { s2a = __fadd2_rn(s2a, e[p]); ss2a = __ffma2_rn(e[p], e[p], ss2a); }
     }
+    const float2 s2 = __fadd2_rn(s2a, s2b), ss2 = __fadd2_rn(ss2a, ss2b);
     const float s = s2.x + s2.y, ss = ss2.x + ss2.y;
     inv_s = rcp_approx(s);
     qs = ss * inv_s;            // q * s
     q = qs * inv_s;
     return k;
 }
+
+// Optional per-pixel statistics cache written by the forward and read by the backward: one
+// float4 per pixel {max logit m, q*s, 1/s^2, argmax class (int bits)} = 16 B/pixel, one
+// coalesced 128-bit store / load per thread and row.  With it the backward skips the max /
+// near-tie mask / sum / reciprocal work (~55 % of its instructions) and needs no reduction
+// over the classes at all; without it (aux == NULL) it recomputes everything from the logits.
 
 // ---------------------------------------------------------------------------------
 // Work partition.  The output is cut into "row units": one unit = one output row of
@@ -210,6 +224,28 @@ __device__ __forceinline__ void hline(float2 (&Hx)[(CT + 1) / 2], const float* s
     }
 }
 
+// Per-segment table of the vertical interpolation parameters (identical for every thread of
+// the CTA): row y -> {ly0, ly1, y0, y1}.  One broadcast LDS.128 per row instead of the
+// I2F / FMUL / F2I / clamp sequence (3 XU-pipe conversions) in every thread.
+constexpr int kRowTabMax = 512;
+__device__ __forceinline__ void fill_row_table(float4* s_rows, const FusedGeo& g, int ys, int ye) {
+    for (int r = threadIdx.x; r < ye - ys; r += kTW) {
+        int y0, y1;
+        float ly0, ly1;
+        src_index(g.sy, ys + r, g.h, y0, y1, ly0, ly1);
+        s_rows[r] = make_float4(ly0, ly1, __int_as_float(y0), __int_as_float(y1));
+    }
+}
+__device__ __forceinline__ void row_params(const float4* s_rows, const FusedGeo& g, bool use_tab, int ys, int y,
+                                           int& y0, int& y1, float& ly0, float& ly1) {
+    if (use_tab) {
+        const float4 v = s_rows[y - ys];
+        ly0 = v.x; ly1 = v.y; y0 = __float_as_int(v.z); y1 = __float_as_int(v.w);
+    } else {
+        src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
+    }
+}
+
 constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
 
 // ------------------------------------------------------------------ K1: forward
@@ -221,10 +257,12 @@ constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
 template <int CT, bool PAD, bool IW, bool HAS_LABEL>
 __global__ void __launch_bounds__(kTW, MSQ_FWD_MINB)
 fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, const int64_t* __restrict__ label,
-                 State st) {
+                 State st, void* __restrict__ aux, float* __restrict__ zero_buf, unsigned zero_count) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long* s_bkt = (unsigned long long*)s_raw;                   // [C][kTW]   (IW only)
-    float* s_tile = (float*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));      // [C][nrm][ncp]
+    const bool use_tab = g.R <= kRowTabMax;
+    float4* s_rows = (float4*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));    // [min(R, kRowTabMax)]
+    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));                   // [C][nrm][ncp]
     __shared__ unsigned s_lab[MSQ_MAX_CLASSES];                               // label= histogram
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
@@ -233,6 +271,12 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
     }
     if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
+    if (zero_buf) {                                    // zero dL/dlogits for the backward's red.adds: no memset launch
+        const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
+        const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
+        for (unsigned i = z0 + tid; i < z1; i += kTW) zero_buf[i] = 0.f;
+    }
+    float4* __restrict__ ax = (float4*)aux;
 
     // units < 2^31 (checked on the host): 32-bit divisions only
     unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
@@ -248,6 +292,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();                                   // previous segment done with s_tile / buckets zeroed
         load_tile(s_tile, lo, g, sp);
+        if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
         __syncthreads();
 
         const bool active = (sp.xs + tid) < sp.xe;
@@ -278,7 +323,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         for (int y = sp.ys; y < sp.ye; ++y) {
             int y0, y1;
             float ly0, ly1;
-            src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
+            row_params(s_rows, g, use_tab, sp.ys, y, y0, y1, ly0, ly1);
             if (y0 != ra) {
                 if (y0 == rb) {
 #pragma unroll
@@ -303,9 +348,10 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
 #pragma unroll
                 for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
             }
-            float inv_s, q, qs;
-            const int k = pixel_stats<CT, IW>(z, e, inv_s, q, qs);
+            float m, inv_s, q, qs;
+            const int k = pixel_stats<CT, IW>(z, e, m, inv_s, q, qs);
             if (active) {
+                if (aux) ax[((long long)sp.n * g.H + y) * g.W + x] = make_float4(m, qs, inv_s * inv_s, __int_as_float(k));
                 if (IW) {
                     if (HAS_LABEL) {
                         const long long lv = label[((long long)sp.n * g.H + y) * g.W + x];
@@ -357,13 +403,15 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
 
 // ------------------------------------------------------------------ K2: backward
 // dL/dz_c = a * p_c * (p_c - q),  a = -2 w[n,k] go / (Nn C)  (IW)   or   -go / (Nn C H W)  (MaxSquare)
-template <int CT, bool PAD, bool IW>
+template <int CT, bool PAD, bool IW, bool CACHED>
 __global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
 fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
                  const float* __restrict__ weights, const float* __restrict__ grad_out, float grad_out_value,
-                 float* __restrict__ grad_lo) {
+                 float* __restrict__ grad_lo, const void* __restrict__ aux) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    float* s_tile = (float*)s_raw;                           // [C][nrm][ncp]
+    const bool use_tab = g.R <= kRowTabMax;
+    float4* s_rows = (float4*)s_raw;                         // [min(R, kRowTabMax)]
+    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));  // [C][nrm][ncp]
     float* s_stage = s_tile + g.C * g.nrm * g.ncp;           // [C][kTW+1]
     float* s_lx0 = s_stage + g.C * (kTW + 1);                // [kTW]
     float* s_lx1 = s_lx0 + kTW;                              // [kTW]
@@ -375,6 +423,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     const float go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
     const float coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
     const int Cd = PAD ? g.C : CT;                           // exact instantiations: constant divisor
+    const float4* __restrict__ ax = (const float4*)aux;
 
     // units < 2^31 (checked on the host): 32-bit divisions only
     unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
@@ -407,6 +456,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         s_j0[tid] = active ? j0 : -1;
         s_j1[tid] = active ? j1 : -1;
         for (int i = tid; i < 4 * g.ncp; i += kTW) s_rng[i] = 0;
+        if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
         __syncthreads();
         if (active) {
             const bool last = (sp.xs + tid + 1 == sp.xe);
@@ -442,10 +492,17 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             __syncthreads();
         };
 
+        // cached statistics of the next row are fetched while the current row is computed
+        const float4* axp = CACHED ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
+        float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CACHED) nx = __ldg(axp);
         for (int y = sp.ys; y < sp.ye; ++y) {
             int y0, y1;
             float ly0, ly1;
-            src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
+            row_params(s_rows, g, use_tab, sp.ys, y, y0, y1, ly0, ly1);
+            const float c_m = nx.x, c_qs = nx.y, c_is2 = nx.z;
+            const int c_k = __float_as_int(nx.w);
+            if (CACHED && y + 1 < sp.ye) { axp += g.W; nx = __ldg(axp); }
             if (y0 != ra) {
                 if (ra >= 0) flush_row(ra, dHa);
                 if (y0 == rb) {
@@ -472,22 +529,37 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                 for (int p = 0; p < CP; ++p) dHb[p] = make_float2(0.f, 0.f);
                 rb = y1;
             }
-            float2 z[CP], e[CP];
-            {
-                const float2 w0 = splat(ly0), w1 = splat(ly1);
+            // g_c = a p_c (p_c - q) = (a / s^2) e_c (e_c - q s)
+            const float2 w0 = splat(ly0), w1 = splat(ly1);
+            if (CACHED) {
+                // max, q*s, 1/s^2 and the argmax class come from the forward's cache: no reduction over
+                // the classes is left, so every class pair streams straight into the accumulators
+                const float a = (IW ? s_coef[c_k] : coef_ms) * c_is2;
+                const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nqs = splat(-c_qs);
+                const float2 l2e = splat(kLog2e), nm = splat(-c_m * kLog2e);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) {
+                    const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+                    const float2 t = __ffma2_rn(zp, l2e, nm);
+                    const float2 ep = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    const float2 v = __fmul2_rn(ep, __fadd2_rn(ep, nqs));
+                    dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                    dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                }
+            } else {
+                float2 z[CP], e[CP];
 #pragma unroll
                 for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
-            }
-            float inv_s, q, qs;
-            const int k = pixel_stats<CT, IW>(z, e, inv_s, q, qs);
-            // g_c = a p_c (p_c - q) = (a / s^2) e_c (e_c - q s)
-            const float a = (IW ? s_coef[k] : coef_ms) * inv_s * inv_s;
-            const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nqs = splat(-qs);
+                float m, inv_s, q, qs;
+                const int k = pixel_stats<CT, IW>(z, e, m, inv_s, q, qs);
+                const float a = (IW ? s_coef[k] : coef_ms) * inv_s * inv_s;
+                const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nqs = splat(-qs);
 #pragma unroll
-            for (int p = 0; p < CP; ++p) {
-                const float2 v = __fmul2_rn(e[p], __fadd2_rn(e[p], nqs));
-                dHa[p] = __ffma2_rn(a0, v, dHa[p]);
-                dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                for (int p = 0; p < CP; ++p) {
+                    const float2 v = __fmul2_rn(e[p], __fadd2_rn(e[p], nqs));
+                    dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                    dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                }
             }
         }
         if (ra >= 0) flush_row(ra, dHa);
@@ -550,17 +622,19 @@ static int occupancy(K kernel, size_t smem, int fallback) {
     return occ;
 }
 
+static size_t row_tab_bytes(const FusedGeo& g) { return g.R <= kRowTabMax ? (size_t)g.R * 16 : 0; }
 static size_t fwd_smem(const FusedGeo& g, bool iw) {
-    return (iw ? (size_t)g.C * kTW * 8 : 0) + (size_t)g.C * g.nrm * g.ncp * sizeof(float);
+    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + (size_t)g.C * g.nrm * g.ncp * sizeof(float);
 }
 static size_t bwd_smem(const FusedGeo& g) {
-    return ((size_t)g.C * g.nrm * g.ncp + (size_t)g.C * (kTW + 1) + 2 * kTW) * sizeof(float) +
+    return row_tab_bytes(g) + ((size_t)g.C * g.nrm * g.ncp + (size_t)g.C * (kTW + 1) + 2 * kTW) * sizeof(float) +
            (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int);
 }
 
 template <int CT, bool PAD>
 static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, const int64_t* label,
-                            float r32, float omr32, int nn, State st, cudaStream_t s) {
+                            float r32, float omr32, int nn, State st, void* aux, float* zero_buf, cudaStream_t s) {
+    const unsigned zero_count = zero_buf ? (unsigned)((size_t)n * C * h * w) : 0u;
     const bool iw = mode != MSQ_MODE_MAXSQUARE;
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
@@ -572,7 +646,7 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
         const size_t smem = fwd_smem(p.g, iw);                                                 \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, label, st);                       \
+        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, label, st, aux, zero_buf, zero_count); \
     } while (0)
     if (!iw) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, false, false>));
     else if (label) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, true>));
@@ -584,9 +658,12 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
 
 template <int CT, bool PAD>
 static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, int nn, State st,
-                            const float* grad_out, float grad_out_value, float* grad_lo, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
-    if (e != cudaSuccess) return (int)e;
+                            const float* grad_out, float grad_out_value, float* grad_lo, const void* aux,
+                            bool grad_is_zeroed, cudaStream_t s) {
+    if (!grad_is_zeroed) {
+        cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
+        if (e != cudaSuccess) return (int)e;
+    }
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
         Plan p;                                                                                \
@@ -597,10 +674,15 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
         const size_t smem = bwd_smem(p.g);                                                     \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, nn, st.weights, grad_out, grad_out_value, grad_lo); \
+        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, nn, st.weights, grad_out, grad_out_value, grad_lo, aux); \
     } while (0)
-    if (mode == MSQ_MODE_MAXSQUARE) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false>));
-    else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, true>));
+    if (mode == MSQ_MODE_MAXSQUARE) {
+        if (aux) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false, true>));
+        else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false, false>));
+    } else {
+        if (aux) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, true, true>));
+        else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, true, false>));
+    }
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
     return 0;
@@ -622,7 +704,8 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
 namespace msq {
 
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
-                       const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, cudaStream_t s) {
+                       const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
+                       float* zero_grad, cudaStream_t s) {
     if (!logits || !accum || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES || h < 1 || w < 1 || out_h < 1 ||
         out_w < 1)
         return MSQ_E_BADARG;
@@ -631,14 +714,14 @@ int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int 
     const State st = carve(accum, out, n, num_class);
     const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, s)
+#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
 
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
-                       float* grad_logits, cudaStream_t s) {
+                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s) {
     if (!logits || !out || !grad_logits || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES ||
         h < 1 || w < 1 || out_h < 1 || out_w < 1)
         return MSQ_E_BADARG;
@@ -646,24 +729,32 @@ int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int 
     if ((((uintptr_t)logits) | ((uintptr_t)grad_logits) | ((uintptr_t)grad_out)) & 3u) return MSQ_E_ALIGN;
     const State st = carve(nullptr, const_cast<void*>(out), n, num_class);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, s)
+#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
 
 }  // namespace msq
 
+extern "C" int64_t msq_fused_aux_bytes(int n, int out_h, int out_w) {
+    if (n < 1 || out_h < 1 || out_w < 1) return 0;
+    const int64_t npix = (int64_t)n * out_h * out_w;
+    return 16 * npix;
+}
+
 extern "C" int msq_fused_fwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                              const int64_t* label, double ratio, int n_images_norm, void* accum, void* out,
-                             msq_stream_t stream) {
+                             void* aux, float* zero_grad, msq_stream_t stream) {
+    if ((((uintptr_t)aux) & 15u) || (((uintptr_t)zero_grad) & 3u)) return MSQ_E_ALIGN;
     return msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, label, ratio, n_images_norm, accum, out,
-                                   (cudaStream_t)stream);
+                                   aux, zero_grad, (cudaStream_t)stream);
 }
 
 extern "C" int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
-                             int n_images_norm, const void* out, const float* grad_out, float* grad_logits,
-                             msq_stream_t stream) {
+                             int n_images_norm, const void* out, const void* aux, const float* grad_out,
+                             float* grad_logits, int grad_is_zeroed, msq_stream_t stream) {
     if (!grad_out) return MSQ_E_BADARG;
+    if (((uintptr_t)aux) & 15u) return MSQ_E_ALIGN;
     return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, 0.f,
-                                   grad_logits, (cudaStream_t)stream);
+                                   grad_logits, aux, grad_is_zeroed, (cudaStream_t)stream);
 }

@@ -21,6 +21,7 @@ struct msq_pipe {
         float* d_grad;
         unsigned char* d_accum;
         unsigned char* d_out;
+        unsigned char* d_aux;
         bool busy;
     } * slots;
     unsigned long long submitted;
@@ -36,6 +37,7 @@ static void pipe_free(msq_pipe* p) {
             if (s.d_grad) cudaFree(s.d_grad);
             if (s.d_accum) cudaFree(s.d_accum);
             if (s.d_out) cudaFree(s.d_out);
+            if (s.d_aux) cudaFree(s.d_aux);
             if (s.done) cudaEventDestroy(s.done);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
@@ -67,6 +69,7 @@ extern "C" int msq_pipe_create(int mode, int n, int num_class, int h, int w, int
         if ((e = cudaMalloc(&s.d_grad, p->lo_bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_accum, (size_t)p->lay.accum_bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_out, (size_t)p->lay.out_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&s.d_aux, (size_t)(16 * (long long)n * out_h * out_w))) != cudaSuccess) break;
         if ((e = cudaMemsetAsync(s.d_accum, 0, (size_t)p->lay.accum_bytes, s.stream)) != cudaSuccess) break;
     }
     if (e != cudaSuccess) { pipe_free(p); return (int)e; }
@@ -97,11 +100,11 @@ extern "C" int msq_pipe_submit(msq_pipe* p, const float* host_logits, float grad
     cudaError_t e;
     if ((e = cudaMemcpyAsync(s.d_logits, host_logits, p->lo_bytes, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) return (int)e;
     rc = fused_fwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, nullptr, p->ratio, 0, s.d_accum,
-                            s.d_out, s.stream);
+                            s.d_out, host_grad ? s.d_aux : nullptr, host_grad ? s.d_grad : nullptr, s.stream);
     if (rc) return rc;
     if (host_grad) {
         rc = fused_bwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, 0, s.d_out, nullptr, grad_scale,
-                                s.d_grad, s.stream);
+                                s.d_grad, s.d_aux, 1, s.stream);
         if (rc) return rc;
         if ((e = cudaMemcpyAsync(host_grad, s.d_grad, p->lo_bytes, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return (int)e;
     }

@@ -35,6 +35,9 @@ from . import _lib
 
 _accum_cache = {}
 
+#: fused mode: let the forward write the 16 B/pixel statistics cache for the backward
+USE_STATS_CACHE = True
+
 
 def _accum_buffer(device, nbytes):
     """Zero-initialised, self-cleaning accumulator buffer, one per (device, stream)."""
@@ -131,23 +134,31 @@ class _ProbLoss(torch.autograd.Function):
 
 
 class _FusedLoss(torch.autograd.Function):
-    """Fused: low-resolution head logits (kernels K1/K2)."""
+    """Fused: low-resolution head logits (kernels K1/K2).  When a gradient will be needed the
+    forward also zero-fills the future dL/dlogits buffer and writes the 16 B/pixel statistics
+    cache that lets the backward skip re-deriving max / argmax / normaliser."""
 
     @staticmethod
     def forward(ctx, logits, label, out_size, mode, num_class, ratio, n_norm, sink):
         n, c, h, w = logits.shape
         H, W = int(out_size[0]), int(out_size[1])
         lo = logits.contiguous()
+        lib = _lib.load()
         lay = _lib.state_layout(n, c)
         accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
         out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
-        _lib.check(_lib.load().msq_fused_fwd(
+        aux = grad = None
+        if logits.requires_grad and torch.is_grad_enabled() and USE_STATS_CACHE:
+            aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device=lo.device)
+            grad = torch.empty_like(lo)
+        _lib.check(lib.msq_fused_fwd(
             mode, lo.data_ptr(), n, c, h, w, H, W, label.data_ptr() if label is not None else None,
-            float(ratio), int(n_norm), accum.data_ptr(), out.data_ptr(), stream))
+            float(ratio), int(n_norm), accum.data_ptr(), out.data_ptr(),
+            aux.data_ptr() if aux is not None else None, grad.data_ptr() if grad is not None else None, stream))
         o = _Outputs(out, n, c)
         sink.append(o)
         ctx.save_for_backward(lo)
-        ctx.out = out
+        ctx.out, ctx.aux, ctx.grad = out, aux, grad
         ctx.cfg = (mode, H, W, n_norm)
         return o.loss
 
@@ -159,11 +170,14 @@ class _FusedLoss(torch.autograd.Function):
         mode, H, W, n_norm = ctx.cfg
         n, c, h, w = lo.shape
         go = _grad_out_ptr(grad_out, lo.device)
-        grad = torch.empty_like(lo)
+        grad, zeroed = ctx.grad, 1
+        ctx.grad = None                       # the pre-zeroed buffer is good for one backward only
+        if grad is None:
+            grad, zeroed = torch.empty_like(lo), 0
         stream = torch.cuda.current_stream(lo.device).cuda_stream
         _lib.check(_lib.load().msq_fused_bwd(
-            mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(), go.data_ptr(),
-            grad.data_ptr(), stream))
+            mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(),
+            ctx.aux.data_ptr() if ctx.aux is not None else None, go.data_ptr(), grad.data_ptr(), zeroed, stream))
         return (grad,) + (None,) * 7
 
 

@@ -19,6 +19,8 @@ lay = _lib.state_layout(N, C)
 accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev)
 out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=dev)
 go = torch.full((), 0.1, device=dev)
+CACHE = os.environ.get("AB_CACHE", "1") == "1"
+auxb = [torch.empty(lib.msq_fused_aux_bytes(N, H, W), dtype=torch.uint8, device=dev) for _ in range(4)]
 st = torch.cuda.current_stream().cuda_stream
 
 def timeit(fn, iters=300, warm=30):
@@ -40,10 +42,12 @@ ok = bool((crit.last_hist.cpu().long() == rh).all()) and abs(l.item() - rl.item(
     (xc.grad.cpu() - rg).abs().max().item() < 1e-4 * rg.abs().max().item()
 res = {}
 for mode, name in ((1, "iw"), (0, "ms")):
-    f = lambda i: lib.msq_fused_fwd(mode, lo[i % POOL].data_ptr(), N, C, h, w, H, W, None, 0.2, 0, accum.data_ptr(), out.data_ptr(), st)
-    b = lambda i: lib.msq_fused_bwd(mode, lo[i % POOL].data_ptr(), N, C, h, w, H, W, 0, out.data_ptr(), go.data_ptr(), gr[i % POOL].data_ptr(), st)
+    f = lambda i: lib.msq_fused_fwd(mode, lo[i % POOL].data_ptr(), N, C, h, w, H, W, None, 0.2, 0, accum.data_ptr(), out.data_ptr(),
+                                    auxb[i % 4].data_ptr() if CACHE else None, gr[i % POOL].data_ptr() if CACHE else None, st)
+    b = lambda i: lib.msq_fused_bwd(mode, lo[i % POOL].data_ptr(), N, C, h, w, H, W, 0, out.data_ptr(),
+                                    auxb[i % 4].data_ptr() if CACHE else None, go.data_ptr(), gr[i % POOL].data_ptr(), 1 if CACHE else 0, st)
     def fb(i): f(i); b(i)
     res[name] = (timeit(f), timeit(b), timeit(fb))
 px = N * H * W
-print(f"{os.path.basename(_lib.LIB_PATH):22s} rows={os.environ.get('AB_ROWS','auto'):>4s} ok={ok} " +
+print(f"{os.path.basename(_lib.LIB_PATH):22s} cache={int(CACHE)} rows={os.environ.get('AB_ROWS','auto'):>4s} ok={ok} " +
       "  ".join(f"{k}: fwd {v[0]:.1f} bwd {v[1]:.1f} f+b {v[2]:.1f} us = {px / v[2] / 1e3:.1f} Gpix/s" for k, v in res.items()), flush=True)

@@ -32,7 +32,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.msq_abi_version() == 1
+    assert lib.msq_abi_version() == 2
     assert lib.msq_error_string(0) == b"success"
     for code in (-1, -2, -3, -4):
         assert lib.msq_error_string(code).startswith(b"msq:")
@@ -64,9 +64,11 @@ def test_argument_validation_without_gpu(lib):
     assert lib.msq_prob_fwd(0, None, 1, 19, 16, None, 0.2, -1, 0, None, None, None) == -1
     assert lib.msq_prob_fwd(7, 16, 1, 19, 16, None, 0.2, -1, 0, 16, 16, None) == -1   # bad mode
     assert lib.msq_prob_bwd(1, None, 1, 19, 16, -1, 0, None, None, None, None) == -1
-    assert lib.msq_fused_fwd(1, None, 1, 19, 4, 4, 8, 8, None, 0.2, 0, None, None, None) == -1
-    assert lib.msq_fused_fwd(1, 16, 1, 19, 8, 8, 4, 4, None, 0.2, 0, 16, 16, None) == -2   # downsampling
-    assert lib.msq_fused_bwd(1, None, 1, 19, 4, 4, 8, 8, 0, None, None, None, None) == -1
+    assert lib.msq_fused_fwd(1, None, 1, 19, 4, 4, 8, 8, None, 0.2, 0, None, None, None, None, None) == -1
+    assert lib.msq_fused_fwd(1, 16, 1, 19, 8, 8, 4, 4, None, 0.2, 0, 16, 16, None, None, None) == -2   # downsampling
+    assert lib.msq_fused_bwd(1, None, 1, 19, 4, 4, 8, 8, 0, None, None, None, None, 0, None) == -1
+    assert lib.msq_fused_aux_bytes(2, 512, 1024) == 16 * 2 * 512 * 1024
+    assert lib.msq_pipe_create(1, 0, 19, 4, 4, 8, 8, 0.2, 2, None) == -1
     assert lib.msq_prob_fwd(0, 18, 1, 19, 16, None, 0.2, -1, 0, 16, 16, None) == -4       # misaligned prob
     assert lib.msq_tune_set(b"no_such_knob", 1) == -1
     assert lib.msq_tune_set(b"conf_agg", 1) == 0

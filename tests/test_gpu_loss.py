@@ -157,6 +157,37 @@ def test_fused_batch_is_mean_of_images_and_deterministic(msq):
     assert abs(sum(parts) - whole.item()) <= 1e-6 * abs(whole.item())
 
 
+def test_fused_backward_with_and_without_stats_cache(msq):
+    """The backward either recomputes max/argmax/normaliser from the logits or reads the 16 B/pixel
+    cache the forward wrote; both must agree (and both are within tolerance of the oracle)."""
+    from maxsquareloss_b200 import loss as L
+    from oracle import loss_math
+    for kind, C, hw, HW in (("iw", 19, (65, 129), (512, 1024)), ("ms", 19, (65, 129), (512, 1024)),
+                            ("iw", 13, (9, 17), (64, 128)), ("iw", 5, (6, 7), (31, 45))):
+        lo = synth.head_logits(2, C, hw, 77, 4.0)
+        ref = (loss_math.fused_iw(lo.numpy(), HW, C, 0.2, 0.1) if kind == "iw" else loss_math.fused_ms(lo.numpy(), HW, 0.1))
+        grads = []
+        try:
+            for use in (True, False):
+                L.USE_STATS_CACHE = use
+                x = lo.cuda().requires_grad_(True)
+                crit = _crit(msq, kind, C)
+                (0.1 * crit(x, out_size=HW)).backward()
+                _grad_close(x.grad, torch.from_numpy(ref["grad_logits"]))
+                grads.append(x.grad.clone())
+        finally:
+            L.USE_STATS_CACHE = True
+        _grad_close(grads[0], grads[1], rtol=1e-5)
+    # retain_graph: the second backward cannot reuse the pre-zeroed buffer
+    x = synth.head_logits(1, 13, (9, 17), 5, 2.0).cuda().requires_grad_(True)
+    loss = msq.IW_MaxSquareloss(-1, 13, 0.2)(x, out_size=(64, 128))
+    loss.backward(retain_graph=True)
+    g1 = x.grad.clone()
+    x.grad = None
+    loss.backward()
+    _grad_close(x.grad, g1, rtol=1e-6)
+
+
 def test_fused_tuning_knob_does_not_change_results(msq):
     from maxsquareloss_b200 import _lib
     lo = synth.head_logits(1, 19, (65, 129), 3, 3.0).cuda()
