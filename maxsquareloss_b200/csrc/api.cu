@@ -17,6 +17,12 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
     __shared__ double s_red[8];
     __shared__ unsigned long long s_cls[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    pdl_trigger();          // the backward may start its prologue now
+    pdl_wait();             // ... but this kernel needs every forward CTA's atomics
+    // thread 0's scalars are fetched first so that their latency overlaps everything else
+    unsigned long long kept_ld = 0ull;
+    unsigned flags_ld = 0u;
+    if (tid == 0) { kept_ld = *st.kept; flags_ld = *st.flags; }
     if (tid < MSQ_MAX_CLASSES) s_cls[tid] = 0ull;
     __syncthreads();
     const int nc = n * C;
@@ -59,12 +65,12 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
     if (tid == 0) {
         double tot = 0.0;
         for (int i = 0; i < nw; ++i) tot += s_red[i];
-        const unsigned long long kept_local = (kept_dense != 0ull) ? kept_dense : *st.kept;
+        const unsigned long long kept_local = (kept_dense != 0ull) ? kept_dense : kept_ld;
         const double scale = (double)n_norm / (double)n;
         double loss;
         if (mode == MSQ_MODE_IW) loss = -tot / ((double)n_norm * (double)C);
         else loss = -tot / (2.0 * (double)kept_local * scale);
-        if (*st.flags & kFlagNonFinite) loss = __longlong_as_double(0x7ff8000000000000LL);
+        if (flags_ld & kFlagNonFinite) loss = __longlong_as_double(0x7ff8000000000000LL);
         *st.loss = (float)loss;
         *st.kept_out = kept_local;
         st.stats[0] = loss;
@@ -76,7 +82,9 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                     unsigned long long kept_dense, cudaStream_t stream) {
     const int warps = n < 8 ? n : 8;
-    finalize_kernel<<<1, 32 * warps, 0, stream>>>(st, mode, n, C, r32, omr32, n_norm, kept_dense);
+    const cudaError_t e = launch_pdl(finalize_kernel, dim3(1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
+                                     n_norm, kept_dense);
+    if (e != cudaSuccess) return (int)e;
     MSQ_CHECK_LAUNCH();
     return 0;
 }

@@ -104,6 +104,14 @@ __device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
+// serialisation attribute may start while its predecessor is still running; it must call
+// pdl_wait() before touching anything the predecessor (transitively: any earlier kernel)
+// produced.  pdl_trigger() lets the successor's CTAs be scheduled as soon as SM resources
+// free up.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -129,15 +137,14 @@ __device__ __forceinline__ unsigned long long to_fix(float qsum) {
 
 // Image-wise class weight, utils/loss.py:95, with the reference's fp32 roundings:
 //   1 / max( fl(hist^r) * fl(total^(1-r)), 1 )     (r and 1-r cast to fp32, as
-//   torch.pow(float32 tensor, python scalar) does).  pow itself is evaluated in
-//   fp64 and rounded once, i.e. it is a <=0.5 ulp fp32 pow.
+//   torch.pow(float32 tensor, python scalar) does).  powf is CUDA's 2-ulp fp32 pow
+//   (torch's CPU pow is Sleef's 1-ulp one): the weights agree to a few ulp, the loss to ~3e-7.
 __device__ __forceinline__ float iw_weight(float hist, float total, float r32, float omr32) {
-    float a = (float)pow((double)hist, (double)r32);
-    float b = (float)pow((double)total, (double)omr32);
-    float m = fmaxf(__fmul_rn(a, b), 1.0f);
+    const float a = powf(hist, r32);
+    const float b = powf(total, omr32);
+    const float m = fmaxf(__fmul_rn(a, b), 1.0f);
     return __fdiv_rn(1.0f, m);
 }
-
 
 // Finalisation kernel (api.cu), launched on the same stream right after a forward kernel:
 // sums the replicas, turns the integer accumulators into the reference's scalar, the
@@ -157,6 +164,25 @@ int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int 
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
                        float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s);
 
+}  // namespace msq
+
+namespace msq {
+// launch with the programmatic-stream-serialisation attribute (see pdl_wait / pdl_trigger)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 }  // namespace msq
 
 #define MSQ_CHECK_LAUNCH()                       \

@@ -266,6 +266,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     __shared__ unsigned s_lab[MSQ_MAX_CLASSES];                               // label= histogram
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
+    pdl_trigger();          // the finalisation kernel may be scheduled as soon as SMs free up
     if (IW) {
 #pragma unroll
         for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
@@ -420,8 +421,12 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     int* s_rng = s_j1 + kTW;                                 // [4][ncp]: start0,end0,start1,end1
     __shared__ float s_coef[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x;
-    const float go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
-    const float coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
+    pdl_trigger();
+    // Launched with programmatic stream serialisation: everything up to pdl_wait() below (index
+    // math, staging the logits tile, the column tables) overlaps the finalisation kernel; the
+    // upstream gradient, the weights, the statistics cache and dL/dlogits are touched only after it.
+    float go = 0.f, coef_ms = 0.f;
+    bool dep_ready = false;
     const int Cd = PAD ? g.C : CT;                           // exact instantiations: constant divisor
     const float4* __restrict__ ax = (const float4*)aux;
 
@@ -437,13 +442,19 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();                                     // previous segment done with all shared arrays
+        load_tile(s_tile, lo, g, sp);
+        if (!dep_ready) {
+            pdl_wait();
+            go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
+            coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
+            dep_ready = true;
+        }
         if (IW && sp.n != coef_img) {
             if (tid < g.C)
                 s_coef[tid] = (float)(-2.0 * (double)weights[sp.n * g.C + tid] * (double)go /
                                       ((double)n_norm * (double)g.C));
             coef_img = sp.n;
         }
-        load_tile(s_tile, lo, g, sp);
 
         const bool active = (sp.xs + tid) < sp.xe;
         const int x = active ? sp.xs + tid : sp.xe - 1;
@@ -674,7 +685,9 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
         const size_t smem = bwd_smem(p.g);                                                     \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, nn, st.weights, grad_out, grad_out_value, grad_lo, aux); \
+        const cudaError_t le = launch_pdl(K, dim3(p.grid), dim3(kTW), smem, s, lo, p.g, n, (unsigned)p.units, nn,       \
+                                          (const float*)st.weights, grad_out, grad_out_value, grad_lo, aux);          \
+        if (le != cudaSuccess) return (int)le;                                                                        \
     } while (0)
     if (mode == MSQ_MODE_MAXSQUARE) {
         if (aux) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false, true>));

@@ -38,6 +38,7 @@ prob_fwd_kernel(const float* __restrict__ prob, int n_img, int C, long long hw, 
     extern __shared__ __align__(16) unsigned long long s_bkt[];      // [C][kProbThreads]  (IW only)
     __shared__ unsigned s_lab[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_trigger();          // the finalisation kernel may be scheduled as soon as SMs free up
     if (IW) {
         for (int c = 0; c < C; ++c) s_bkt[c * kProbThreads + tid] = 0ull;
         if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;

@@ -92,7 +92,7 @@ def test_fused_vs_oracle(msq, C, hw, HW, N, scale, kind):
         # arithmetic (oracle/bilinear.py), which is what the kernel implements
         assert crit.last_hist.cpu().numpy().tolist() == r["hist"].tolist()
         w = loss_math.weights_fp32(r["hist"], 0.2)
-        assert np.abs(crit.last_weights.cpu().numpy() - w).max() <= 1e-6 * np.abs(w).max()   # fp32 pow differs by a few ulp between libraries
+        assert np.abs(crit.last_weights.cpu().numpy() - w).max() <= 2e-6 * np.abs(w).max()   # fp32 pow differs by a few ulp between libraries
 
 
 def test_fused_vs_torch_cuda_eager_chain(msq):
