@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSQ_ABI_VERSION 2
+#define MSQ_ABI_VERSION 3
 #define MSQ_MAX_CLASSES 32          /* reference uses 13 / 16 / 19 */
 
 #define MSQ_E_BADARG   (-1)         /* null pointer, non-positive size, C > MSQ_MAX_CLASSES */
@@ -64,6 +64,8 @@ const char* msq_error_string(int code);
  *   hist   uint32[R][N*C] per-image class histogram being accumulated
  *   flags  uint32       bit0: a non-finite value was seen (loss becomes NaN)
  *   ticket uint32       reserved
+ *   ce     uint64[R]    multi-level guidance: sum of -log p2[label_2], 2^-32 fixed point
+ *   nvalid uint64[R]    multi-level guidance: pixels with label_2 != -1
  *
  * OUTPUTS (`out`, out_bytes): written by the forward, read by the backward.
  *   sum_out   float64[N]   per-image sum of q (diagnostics / multi-GPU reduction)
@@ -76,11 +78,18 @@ const char* msq_error_string(int code);
  *                          this vector yields the global loss and class histogram
  *                          when images are sharded over ranks (counts < 2^53 are
  *                          exact in fp64)
+ *   nvalid_out uint64      msq_multi_fwd: number of pixels with label_2 != -1
+ *   loss2     float32      msq_multi_fwd: CrossEntropyLoss(ignore_index=-1)(head 2, label_2)
+ *   ce_out    float64      msq_multi_fwd: sum over those pixels of -log softmax(head 2)[label_2];
+ *                          loss2 = ce_out / nvalid_out.  When images are sharded over ranks the
+ *                          caller all-reduces {ce_out, nvalid_out} and stores the global count back
+ *                          into nvalid_out before msq_guidance_bwd (which divides by it)
  * ------------------------------------------------------------------------- */
 typedef struct msq_state_layout {
-    int64_t sumsq_off, kept_off, hist_off, flags_off, ticket_off;   /* into accum */
+    int64_t sumsq_off, kept_off, hist_off, flags_off, ticket_off, ce_off, nvalid_off;   /* into accum */
     int64_t accum_bytes;
-    int64_t sum_out_off, kept_out_off, loss_off, weights_off, hist_out_off, stats_off;   /* into out */
+    int64_t sum_out_off, kept_out_off, loss_off, weights_off, hist_out_off, stats_off,
+            nvalid_out_off, loss2_off, ce_out_off;                                                /* into out */
     int64_t out_bytes;
 } msq_state_layout;
 
@@ -144,6 +153,30 @@ int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, in
                   int out_h, int out_w, int n_images_norm, const void* out,
                   const void* aux /* nullable */, const float* grad_out, float* grad_logits,
                   int grad_is_zeroed, msq_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Multi-level self-produced guidance ("MaxSquare+IW+Multi", BASELINE config 3): the inline
+ * trainer code tools/solve_gta5.py:183,192,206-215 == tools/solve_crosscity.py:235-243,
+ * fused with the head-1 adaptation loss, from the LOW-resolution outputs of both heads.
+ *   loss   (out.loss)  = msq_fused_fwd's loss on head 1 (mode, ratio)
+ *   label_2            = (max P1 > threshold || max P2 > threshold) ? argmax_c (P1+P2)/2 : -1
+ *   loss2  (out.loss2) = nn.CrossEntropyLoss(ignore_index=-1)(up(head 2), label_2)
+ *                        mean over the out.nvalid_out pixels with label_2 != -1 (NaN if none)
+ *   aux1 / aux2        float4-per-pixel caches (msq_fused_aux_bytes each, nullable) for
+ *                      msq_fused_bwd (head 1) and msq_guidance_bwd (head 2, required there)
+ *   zero_grad1/2       optional dL/dlogits buffers to zero-fill on the side
+ *   label2_out         optional int64 [N,H,W]: the pseudo-label map (bit-exact vs the reference)
+ * The caller combines  lambda_target*loss + lambda_seg*lambda_target*loss2  (solve_gta5.py:199,213).
+ * ------------------------------------------------------------------------- */
+int msq_multi_fwd(int mode, const float* logits1, const float* logits2, int n, int num_class,
+                  int h, int w, int out_h, int out_w, double ratio, double threshold,
+                  int n_images_norm, void* accum, void* out, void* aux1, void* aux2,
+                  float* zero_grad1, float* zero_grad2, int64_t* label2_out, msq_stream_t stream);
+
+/* d(loss2)/d(logits2) = grad_out/nvalid * (softmax - onehot(label_2)) through the bilinear adjoint. */
+int msq_guidance_bwd(const float* logits2, int n, int num_class, int h, int w, int out_h, int out_w,
+                     const void* out, const void* aux2, const float* grad_out, float* grad_logits2,
+                     int grad_is_zeroed, msq_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Evaluation: Eval.__generate_matrix / add_batch (utils/eval.py:109-121).

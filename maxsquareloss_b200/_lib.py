@@ -16,14 +16,15 @@ MODE_IW = 1
 
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
-           "msq_fused_fwd", "msq_fused_bwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set",
+           "msq_fused_fwd", "msq_fused_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set",
            "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
 class StateLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
-        "sumsq_off", "kept_off", "hist_off", "flags_off", "ticket_off", "accum_bytes",
-        "sum_out_off", "kept_out_off", "loss_off", "weights_off", "hist_out_off", "stats_off", "out_bytes")]
+        "sumsq_off", "kept_off", "hist_off", "flags_off", "ticket_off", "ce_off", "nvalid_off", "accum_bytes",
+        "sum_out_off", "kept_out_off", "loss_off", "weights_off", "hist_out_off", "stats_off",
+        "nvalid_out_off", "loss2_off", "ce_out_off", "out_bytes")]
 
 
 _lib = None
@@ -60,6 +61,10 @@ def load():
         lib.msq_fused_fwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, vp, dbl, i32, vp, vp, vp, vp, vp]
         lib.msq_fused_bwd.restype = i32
         lib.msq_fused_bwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+        lib.msq_multi_fwd.restype = i32
+        lib.msq_multi_fwd.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.msq_guidance_bwd.restype = i32
+        lib.msq_guidance_bwd.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]
         lib.msq_fused_aux_bytes.restype = i64
         lib.msq_fused_aux_bytes.argtypes = [i32, i32, i32]
         lib.msq_confusion_i64.restype = i32
@@ -78,7 +83,7 @@ def load():
         lib.msq_pipe_drain.argtypes = [vp]
         lib.msq_pipe_destroy.restype = None
         lib.msq_pipe_destroy.argtypes = [vp]
-        if lib.msq_abi_version() != 2:
+        if lib.msq_abi_version() != 3:
             raise RuntimeError("libmsq_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

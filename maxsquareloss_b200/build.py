@@ -14,8 +14,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmsq_b200.so")
-SOURCES = ["api.cu", "confusion.cu", "prob_loss.cu", "fused_loss.cu", "host_pipe.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(PKG), "include", "msq_b200.h")]
+SOURCES = ["api.cu", "confusion.cu", "prob_loss.cu", "fused_loss.cu", "guidance.cu", "host_pipe.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "fused_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "msq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC",
               # share libcudart.so.12 with PyTorch: one runtime instance => one notion of the current
@@ -39,19 +39,43 @@ def is_stale():
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """Compile every CUDA source into one shared library.  Returns its path.
-    ``defines``/``out`` build an experimental variant next to the default library."""
+    """Compile every CUDA source (one nvcc per file, in parallel) and link one shared library.
+    Returns its path.  ``defines``/``out`` build an experimental variant next to the default library."""
+    from concurrent.futures import ThreadPoolExecutor
     out = out or LIB
     if not force and not defines and not is_stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
-          ["-o", out + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(LIBDIR, "obj" + ("_" + "_".join(defines).replace("=", "-") if defines else ""))
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    cflags = [f for f in NVCC_FLAGS if f not in ("--shared",)]
+    cflags = cflags[:cflags.index("-cudart")]            # link-only flags stay out of the compile step
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        path = os.path.join(CSRC, src)
+        deps = [path] + HEADERS
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+            return obj, None
+        cmd = [nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+              ["-c", "-o", obj, path]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
     if verbose:
-        sys.stderr.write(res.stderr)
+        for _, err in results:
+            if err:
+                sys.stderr.write(err)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared",
+            "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", out + ".tmp"] + [o for o, _ in results]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     os.replace(out + ".tmp", out)
     return out
 

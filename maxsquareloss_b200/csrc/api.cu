@@ -13,7 +13,8 @@ namespace msq {
 
 // one warp per image, one lane per class (C <= 32)
 __global__ void __launch_bounds__(256)
-finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_norm, unsigned long long kept_dense) {
+finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_norm, unsigned long long kept_dense,
+                int multi) {
     __shared__ double s_red[8];
     __shared__ unsigned long long s_cls[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
@@ -23,6 +24,9 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
     unsigned long long kept_ld = 0ull;
     unsigned flags_ld = 0u;
     if (tid == 0) { kept_ld = *st.kept; flags_ld = *st.flags; }
+    // multi-level guidance: cross-entropy sum and valid-pixel count, one replica per lane of warp 0
+    unsigned long long ce_ld = 0ull, nv_ld = 0ull;
+    if (multi && tid < kRep) { ce_ld = st.ce[tid]; nv_ld = st.nvalid[tid]; st.ce[tid] = 0ull; st.nvalid[tid] = 0ull; }
     if (tid < MSQ_MAX_CLASSES) s_cls[tid] = 0ull;
     __syncthreads();
     const int nc = n * C;
@@ -56,6 +60,10 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
         for (int o = 16; o > 0; o >>= 1) simg += __shfl_xor_sync(0xffffffffu, simg, o);
         if (lane == 0) st.sum_out[img] = simg;
     }
+    if (multi && wid == 0) {
+        ce_ld = warp_sum_u64(ce_ld);
+        nv_ld = warp_sum_u64(nv_ld);
+    }
     if (lane < C && cls_tot) atomicAdd(&s_cls[lane], cls_tot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -74,16 +82,23 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
         *st.loss = (float)loss;
         *st.kept_out = kept_local;
         st.stats[0] = loss;
+        if (multi) {       // nn.CrossEntropyLoss(ignore_index=-1): mean over the valid pixels, 0/0 = NaN as in torch
+            double l2 = ((double)ce_ld * kInvFix) / (double)nv_ld;
+            if (flags_ld & kFlagNonFinite) l2 = __longlong_as_double(0x7ff8000000000000LL);
+            *st.loss2 = (float)l2;
+            *st.nvalid_out = nv_ld;
+            *st.ce_out = (double)ce_ld * kInvFix;
+        }
         *st.kept = 0ull;                       // self-clean
         *st.flags = 0u;
     }
 }
 
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                    unsigned long long kept_dense, cudaStream_t stream) {
+                    unsigned long long kept_dense, cudaStream_t stream, int multi) {
     const int warps = n < 8 ? n : 8;
     const cudaError_t e = launch_pdl(finalize_kernel, dim3(1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
-                                     n_norm, kept_dense);
+                                     n_norm, kept_dense, multi);
     if (e != cudaSuccess) return (int)e;
     MSQ_CHECK_LAUNCH();
     return 0;

@@ -32,6 +32,12 @@ struct State {
     double* sum_out;
     unsigned long long* kept_out;
     double* stats;
+    // multi-level guidance (guidance.cu)
+    unsigned long long* ce;        // accum: [kRep] sum of -log p2[label_2] in 2^-32 fixed point
+    unsigned long long* nvalid;    // accum: [kRep] number of pixels with label_2 != -1
+    float* loss2;                  // out
+    unsigned long long* nvalid_out;
+    double* ce_out;                // out: sum of -log p2[label_2] over the valid pixels (for sharded means)
 };
 
 __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -44,6 +50,9 @@ inline msq_state_layout make_layout(int n, int c) {
     L.hist_off = off;   off += nc * 4 * kRep;
     L.flags_off = off;  off += 4;
     L.ticket_off = off; off += 4;
+    off = align_up(off, 8);
+    L.ce_off = off;     off += 8 * kRep;
+    L.nvalid_off = off; off += 8 * kRep;
     L.accum_bytes = align_up(off, 16);
     off = 0;
     L.sum_out_off = off;  off += (int64_t)n * 8;
@@ -54,6 +63,10 @@ inline msq_state_layout make_layout(int n, int c) {
     L.hist_out_off = off; off += nc * 4;
     off = align_up(off, 16);
     L.stats_off = off;    off += (int64_t)(1 + c) * 8;
+    L.nvalid_out_off = off; off += 8;
+    L.loss2_off = off;    off += 4;
+    off = align_up(off, 8);
+    L.ce_out_off = off;   off += 8;
     L.out_bytes = align_up(off, 16);
     return L;
 }
@@ -74,6 +87,11 @@ inline State carve(void* accum, void* out, int n, int c) {
     s.sum_out = (double*)(o + L.sum_out_off);
     s.kept_out = (unsigned long long*)(o + L.kept_out_off);
     s.stats = (double*)(o + L.stats_off);
+    s.ce = (unsigned long long*)(a + L.ce_off);
+    s.nvalid = (unsigned long long*)(a + L.nvalid_off);
+    s.loss2 = (float*)(o + L.loss2_off);
+    s.nvalid_out = (unsigned long long*)(o + L.nvalid_out_off);
+    s.ce_out = (double*)(o + L.ce_out_off);
     return s;
 }
 
@@ -154,7 +172,7 @@ __device__ __forceinline__ float iw_weight(float hist, float total, float r32, f
 //   MaxSquare (utils/loss.py:118):     loss = -(sum q) / (2 * kept)
 // Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                    unsigned long long kept_dense, cudaStream_t stream);
+                    unsigned long long kept_dense, cudaStream_t stream, int multi = 0);
 
 // fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,

@@ -1,0 +1,651 @@
+// Shared device code of the fused kernels (fused_loss.cu, guidance.cu): geometry, tile
+// staging, per-pixel softmax statistics, the forward / backward column-walk kernels and the
+// host-side launch planning.
+#pragma once
+#include "common.cuh"
+
+
+namespace msq {
+
+constexpr int kTW = 128;                        // output columns (= threads) per CTA
+#ifndef MSQ_FWD_MINB
+#define MSQ_FWD_MINB 4                          // co-resident CTAs per SM the forward is compiled for
+#endif
+#ifndef MSQ_BWD_MINB
+#define MSQ_BWD_MINB 4
+#endif
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kNearTie = 2.384185791015625e-07f;   // 2^-22, see resolve_ties
+constexpr float kPadLogit = -1.0e30f;           // logits of padded classes (C < CT)
+
+// ATen/native/UpSample.h area_pixel_compute_source_index + guard_index_and_lambda
+// (align_corners=True): src = scale*dst in fp32, i0 = trunc, lambda1 = src - i0.
+__host__ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0,
+                                                   float& l1) {
+#ifdef __CUDA_ARCH__
+    const float src = __fmul_rn(scale, (float)dst);
+#else
+    volatile float srcv = scale * (float)dst;
+    const float src = srcv;
+#endif
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    float lam = src - (float)i0;
+    lam = lam < 0.f ? 0.f : (lam > 1.f ? 1.f : lam);
+    l1 = lam;
+    l0 = 1.0f - lam;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+}
+
+struct FusedGeo {
+    int C, h, w, H, W;
+    float sy, sx;        // (in-1)/(out-1) in fp32 (0 when out == 1)
+    int R;               // output rows per strip
+    int nrm, ncp;        // max low-res rows / cols any strip touches (tile pitch)
+};
+
+// Exact replica of what torch's softmax + max do when two interpolated logits are
+// within a few ulps: p_c = expf(z_c - m) / sum_k expf(z_k - m) in class order, then
+// the FIRST class whose p equals the maximum p (= 1/sum) wins (utils/loss.py:84).
+// Only called for pixels where another class is within 2^-22 of the maximum.
+template <int CT>
+__device__ __noinline__ int resolve_ties(const float* z, float m) {
+    float e[CT];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) { e[c] = expf(z[c] - m); s += e[c]; }
+    const float pm = __fdiv_rn(1.0f, s);
+    int k = -1;
+#pragma unroll
+    for (int c = CT - 1; c >= 0; --c) if (__fdiv_rn(e[c], s) == pm) k = c;
+    return k;
+}
+
+// Classes are processed two at a time with Blackwell's packed fp32x2 instructions
+// (fma.rn.f32x2 / mul.f32x2 / add.f32x2, sm_100+): the kernels are instruction-issue
+// bound, and one FFMA2 does the work of two FFMAs with identical IEEE rounding per
+// lane, so bit-exactness of the interpolated logits is unaffected.  Class c lives in
+// lane (c & 1) of pair (c >> 1); an odd class count leaves one padding lane.
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float lane_of(const float2& v, int c) { return (c & 1) ? v.y : v.x; }
+
+// Per-pixel softmax statistics from the interpolated logits z[] (pairs):
+//   e[c] = 2^((z_c - m) log2 e), inv_s = 1/s with s = sum e, q = sum_c p_c^2, qs = q*s;
+//   returns the argmax class.
+template <int CT, bool NEED_ARG>
+__device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], float2 (&e)[(CT + 1) / 2], float& m_out,
+                                           float& inv_s, float& q, float& qs) {
+    constexpr int CP = (CT + 1) / 2;
+    float m = z[0].x;
+#pragma unroll
+    for (int c = 1; c < CT; ++c) m = fmaxf(m, lane_of(z[c >> 1], c));
+    m_out = m;
+    int k = 0;
+    if (NEED_ARG) {
+        const float thr = m - kNearTie;
+        unsigned mask_a = 0u, mask_b = 0u;              // two chains: the ORs are serial per register
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {                  // one FSETP + one predicated LOP3 per class
+            if (c & 1)
+                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(mask_b) : "f"(z[c >> 1].y), "f"(thr), "r"(1u << c));
+            else
+                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(mask_a) : "f"(z[c >> 1].x), "f"(thr), "r"(1u << c));
+        }
+        const unsigned mask = mask_a | mask_b;
+        k = __ffs(mask) - 1;
+        if (mask & (mask - 1u)) {                       // more than one class within 2^-22 of the max
+            asm volatile("" ::: "memory");              // keep the spill of z[] inside this cold branch
+            float zl[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) zl[c] = lane_of(z[c >> 1], c);
+            k = resolve_ties<CT>(zl, m);
+        }
+        if (k < 0) k = 0;                               // NaN logits: reference yields NaN loss anyway
+    }
+    const float2 l2e = splat(kLog2e), nm = splat(-m * kLog2e);
+    float2 s2a = make_float2(0.f, 0.f), s2b = s2a, ss2a = s2a, ss2b = s2a;
+#pragma unroll
+    for (int p = 0; p < CP; ++p) {
+        const float2 t = __ffma2_rn(z[p], l2e, nm);
+        e[p] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        if (p & 1) { s2b = __fadd2_rn(s2b, e[p]); ss2b = __ffma2_rn(e[p], e[p], ss2b); }
+        else { s2a = __fadd2_rn(s2a, e[p]); ss2a = __ffma2_rn(e[p], e[p], ss2a); }
+    }
+    const float2 s2 = __fadd2_rn(s2a, s2b), ss2 = __fadd2_rn(ss2a, ss2b);
+    const float s = s2.x + s2.y, ss = ss2.x + ss2.y;
+    inv_s = rcp_approx(s);
+    qs = ss * inv_s;            // q * s
+    q = qs * inv_s;
+    return k;
+}
+
+// Optional per-pixel statistics cache written by the forward and read by the backward: one
+// float4 per pixel {max logit m, q*s, 1/s^2, argmax class (int bits)} = 16 B/pixel, one
+// coalesced 128-bit store / load per thread and row.  With it the backward skips the max /
+// near-tie mask / sum / reciprocal work (~55 % of its instructions) and needs no reduction
+// over the classes at all; without it (aux == NULL) it recomputes everything from the logits.
+
+// ---------------------------------------------------------------------------------
+// Work partition.  The output is cut into "row units": one unit = one output row of
+// one kTW-wide column tile of one image, numbered u = (n*TX + tx)*H + y.  The grid
+// has exactly as many CTAs as fit on the chip at once (148 x occupancy, one wave, no
+// tail) and CTA b owns the contiguous unit range [b*U/G, (b+1)*U/G): every CTA gets
+// the same number of rows to within one.  A range is walked as 1..2 "segments"
+// (it may cross a column-tile boundary); per segment the low-res tile is staged in
+// shared memory and each thread walks its column down the rows.
+// ---------------------------------------------------------------------------------
+struct Strip {
+    int n, xs, xe, ys, ye;        // output extent of this segment
+    int c_lo, r_lo, nc, nr;       // low-res tile origin / extent
+};
+
+__device__ __forceinline__ Strip make_strip(const FusedGeo& g, int col, int TX, int ys, int ye) {
+    Strip s;
+    s.n = col / TX;
+    s.xs = (col - s.n * TX) * kTW;
+    s.xe = min(g.W, s.xs + kTW);
+    s.ys = ys;
+    s.ye = ye;
+    int i0, i1;
+    float l0, l1;
+    src_index(g.sx, s.xs, g.w, i0, i1, l0, l1);
+    s.c_lo = i0;
+    src_index(g.sx, s.xe - 1, g.w, i0, i1, l0, l1);
+    s.nc = i1 - s.c_lo + 1;
+    src_index(g.sy, s.ys, g.h, i0, i1, l0, l1);
+    s.r_lo = i0;
+    src_index(g.sy, s.ye - 1, g.h, i0, i1, l0, l1);
+    s.nr = i1 - s.r_lo + 1;
+    if (s.nc > g.ncp || s.nr > g.nrm) __trap();      // host sized the tile from the same arithmetic
+    return s;
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// Stage the low-res tile [C][nr][nc] (pitches nrm, ncp) in shared memory with
+// cp.async (LDGSTS): every element is in flight at once, no register staging.
+// Thread t owns tile element (t / nc, t % nc) of every class: one integer division per
+// segment, then one cp.async per class.
+__device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict__ lo, const FusedGeo& g,
+                                          const Strip& s) {
+    const int cells = s.nr * s.nc;
+    const int hw = g.h * g.w, cstride = g.nrm * g.ncp;
+    const float* base = lo + ((long long)s.n * g.C * g.h + s.r_lo) * g.w + s.c_lo;
+    for (int t = threadIdx.x; t < cells; t += kTW) {
+        const int r = t / s.nc, j = t - r * s.nc;
+        const float* src = base + r * g.w + j;
+        float* dst = s_tile + r * g.ncp + j;
+#pragma unroll 4
+        for (int c = 0; c < g.C; ++c) cp_async4(dst + c * cstride, src + (long long)c * hw);
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// t_r[c] = fma(A[c][r][x0], lx0, A[c][r][x1] * lx1)   (horizontal pass of ATen's formula)
+template <int CT, bool PAD>
+__device__ __forceinline__ void hline(float2 (&Hx)[(CT + 1) / 2], const float* s_tile, const FusedGeo& g, int rr,
+                                      int j0, int j1, float lx0, float lx1) {
+    constexpr int CP = (CT + 1) / 2;
+    const float* row = s_tile + rr * g.ncp;
+    const int cstride = g.nrm * g.ncp;
+    const float2 l0 = splat(lx0), l1 = splat(lx1);
+#pragma unroll
+    for (int p = 0; p < CP; ++p) {
+        const int c0 = 2 * p, c1 = 2 * p + 1;
+        const bool in0 = !PAD || c0 < g.C;
+        const bool in1 = (c1 < CT) && (!PAD || c1 < g.C);
+        const float2 a = make_float2(in0 ? row[c0 * cstride + j0] : kPadLogit, in1 ? row[c1 * cstride + j0] : kPadLogit);
+        const float2 b = make_float2(in0 ? row[c0 * cstride + j1] : kPadLogit, in1 ? row[c1 * cstride + j1] : kPadLogit);
+        Hx[p] = __ffma2_rn(a, l0, __fmul2_rn(b, l1));
+    }
+}
+
+// Per-segment table of the vertical interpolation parameters (identical for every thread of
+// the CTA): row y -> {ly0, ly1, y0, y1}.  One broadcast LDS.128 per row instead of the
+// I2F / FMUL / F2I / clamp sequence (3 XU-pipe conversions) in every thread.
+constexpr int kRowTabMax = 512;
+__device__ __forceinline__ void fill_row_table(float4* s_rows, const FusedGeo& g, int ys, int ye) {
+    for (int r = threadIdx.x; r < ye - ys; r += kTW) {
+        int y0, y1;
+        float ly0, ly1;
+        src_index(g.sy, ys + r, g.h, y0, y1, ly0, ly1);
+        s_rows[r] = make_float4(ly0, ly1, __int_as_float(y0), __int_as_float(y1));
+    }
+}
+__device__ __forceinline__ void row_params(const float4* s_rows, const FusedGeo& g, bool use_tab, int ys, int y,
+                                           int& y0, int& y1, float& ly0, float& ly1) {
+    if (use_tab) {
+        const float4 v = s_rows[y - ys];
+        ly0 = v.x; ly1 = v.y; y0 = __float_as_int(v.z); y1 = __float_as_int(v.w);
+    } else {
+        src_index(g.sy, y, g.h, y0, y1, ly0, ly1);
+    }
+}
+
+constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
+
+// ------------------------------------------------------------------ K1: forward
+// IW: every thread keeps, per class, a private packed accumulator in shared memory
+//     (count << 48 | sum of q in 2^-32 fixed point): a class change along the column
+//     costs one conflict-free LDS.64/STS.64 pair, no atomics.  The buckets are reduced
+//     by warp shuffles at the end of the segment and merged with one global atomic per
+//     class and warp.
+template <int CT, bool PAD, bool IW, bool HAS_LABEL>
+__global__ void __launch_bounds__(kTW, MSQ_FWD_MINB)
+fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, const int64_t* __restrict__ label,
+                 State st, void* __restrict__ aux, float* __restrict__ zero_buf, unsigned zero_count) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* s_bkt = (unsigned long long*)s_raw;                   // [C][kTW]   (IW only)
+    const bool use_tab = g.R <= kRowTabMax;
+    float4* s_rows = (float4*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));    // [min(R, kRowTabMax)]
+    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));                   // [C][nrm][ncp]
+    __shared__ unsigned s_lab[MSQ_MAX_CLASSES];                               // label= histogram
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
+    pdl_trigger();          // the finalisation kernel may be scheduled as soon as SMs free up
+    if (IW) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
+    }
+    if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
+    if (zero_buf) {                                    // zero dL/dlogits for the backward's red.adds: no memset launch
+        const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
+        const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
+        for (unsigned i = z0 + tid; i < z1; i += kTW) zero_buf[i] = 0.f;
+    }
+    float4* __restrict__ ax = (float4*)aux;
+
+    // units < 2^31 (checked on the host): 32-bit divisions only
+    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
+    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
+    unsigned long long ms_acc = 0ull;
+    bool bad = false;
+    while (u < u_end) {
+        const unsigned col = u / (unsigned)g.H;
+        const int ys = (int)(u - col * (unsigned)g.H);
+        const int ye = (int)min((unsigned)g.H, (unsigned)ys + (u_end - u));
+        u += (unsigned)(ye - ys);
+        const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
+        __syncthreads();                                   // previous segment done with s_tile / buckets zeroed
+        load_tile(s_tile, lo, g, sp);
+        if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
+        __syncthreads();
+
+        const bool active = (sp.xs + tid) < sp.xe;
+        const int x = active ? sp.xs + tid : sp.xe - 1;
+        int x0, x1;
+        float lx0, lx1;
+        src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
+        const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
+
+        constexpr int CP = (CT + 1) / 2;
+        float2 Ha[CP], Hb[CP];
+        int ra = -1, rb = -1;
+        int run_k = -1;
+        unsigned run_cnt = 0u;
+        float run_q = 0.f;
+        auto flush = [&]() {
+            if (run_cnt) {
+                bad |= !(fabsf(run_q) < 3.0e38f);
+                if (IW) {
+                    const unsigned long long inc = to_fix(run_q) + (HAS_LABEL ? 0ull : ((unsigned long long)run_cnt << 48));
+                    s_bkt[run_k * kTW + tid] += inc;
+                } else {
+                    ms_acc += to_fix(run_q);
+                }
+            }
+        };
+
+        for (int y = sp.ys; y < sp.ye; ++y) {
+            int y0, y1;
+            float ly0, ly1;
+            row_params(s_rows, g, use_tab, sp.ys, y, y0, y1, ly0, ly1);
+            if (y0 != ra) {
+                if (y0 == rb) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) Ha[p] = Hb[p];
+                } else {
+                    hline<CT, PAD>(Ha, s_tile, g, y0 - sp.r_lo, j0, j1, lx0, lx1);
+                }
+                ra = y0;
+            }
+            if (y1 != rb) {
+                if (y1 == ra) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) Hb[p] = Ha[p];
+                } else {
+                    hline<CT, PAD>(Hb, s_tile, g, y1 - sp.r_lo, j0, j1, lx0, lx1);
+                }
+                rb = y1;
+            }
+            float2 z[CP], e[CP];
+            {
+                const float2 w0 = splat(ly0), w1 = splat(ly1);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+            }
+            float m, inv_s, q, qs;
+            const int k = pixel_stats<CT, IW>(z, e, m, inv_s, q, qs);
+            if (active) {
+                if (aux) ax[((long long)sp.n * g.H + y) * g.W + x] = make_float4(m, qs, inv_s * inv_s, __int_as_float(k));
+                if (IW) {
+                    if (HAS_LABEL) {
+                        const long long lv = label[((long long)sp.n * g.H + y) * g.W + x];
+                        if (lv >= 0 && lv < g.C) atomicAdd(&s_lab[(int)lv], 1u);
+                    }
+                    if (k == run_k) { run_cnt++; run_q += q; }
+                    else { flush(); run_k = k; run_cnt = 1u; run_q = q; }
+                } else {
+                    run_k = 0; run_cnt++; run_q += q;
+                }
+            }
+        }
+        flush();
+
+        if (IW) {
+            // reduce the private buckets of this segment: warp w owns classes w, w+4, ...
+            __syncthreads();
+            for (int c = wid; c < g.C; c += kTW / 32) {
+                unsigned cnt = 0u;
+                unsigned long long sum = 0ull;
+#pragma unroll
+                for (int t = 0; t < kTW / 32; ++t) {
+                    const unsigned long long v = s_bkt[c * kTW + t * 32 + lane];
+                    s_bkt[c * kTW + t * 32 + lane] = 0ull;
+                    cnt += (unsigned)(v >> 48);
+                    sum += v & kBktMask;
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                sum = warp_sum_u64(sum);
+                if (lane == 0) {
+                    if (HAS_LABEL) cnt = s_lab[c];
+                    if (cnt) atomicAdd(&st.hist[rep_off + sp.n * g.C + c], cnt);
+                    if (sum) atomicAdd(&st.sumsq[rep_off + sp.n * g.C + c], sum);
+                    if (HAS_LABEL) s_lab[c] = 0u;
+                }
+            }
+        } else {
+            // MaxSquare: hand the running sum over when the next segment belongs to another image
+            const int next_n = (u < u_end) ? (int)((u / (unsigned)g.H) / TX) : -1;
+            if (next_n != sp.n) {
+                ms_acc = warp_sum_u64(ms_acc);
+                if (lane == 0 && ms_acc) atomicAdd(&st.sumsq[rep_off + sp.n * g.C], ms_acc);
+                ms_acc = 0ull;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(st.flags, kFlagNonFinite);
+}
+
+// ------------------------------------------------------------------ K2: backward
+// dL/dz_c = a * p_c * (p_c - q),  a = -2 w[n,k] go / (Nn C)  (IW)   or   -go / (Nn C H W)  (MaxSquare)
+// GUIDE (needs CACHED): instead of the loss gradient, the gradient of the multi-level guidance
+// cross-entropy on this head (tools/solve_gta5.py:213, nn.CrossEntropyLoss(ignore_index=-1)):
+//   dL/dz_c = (go / n_valid) * (p_c - [c == label_2])   for pixels with label_2 != -1
+// with {m, 1/s, label_2} read from the float4 cache msq_multi_fwd wrote for head 2.
+template <int CT, bool PAD, bool IW, bool CACHED, bool GUIDE = false>
+__global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
+fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
+                 const float* __restrict__ weights, const float* __restrict__ grad_out, float grad_out_value,
+                 float* __restrict__ grad_lo, const void* __restrict__ aux,
+                 const unsigned long long* __restrict__ nvalid = nullptr) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const bool use_tab = g.R <= kRowTabMax;
+    float4* s_rows = (float4*)s_raw;                         // [min(R, kRowTabMax)]
+    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));  // [C][nrm][ncp]
+    float* s_stage = s_tile + g.C * g.nrm * g.ncp;           // [C][kTW+1]
+    float* s_lx0 = s_stage + g.C * (kTW + 1);                // [kTW]
+    float* s_lx1 = s_lx0 + kTW;                              // [kTW]
+    int* s_j0 = (int*)(s_lx1 + kTW);                         // [kTW]
+    int* s_j1 = s_j0 + kTW;                                  // [kTW]
+    int* s_rng = s_j1 + kTW;                                 // [4][ncp]: start0,end0,start1,end1
+    __shared__ float s_coef[MSQ_MAX_CLASSES];
+    const int tid = threadIdx.x;
+    pdl_trigger();
+    // Launched with programmatic stream serialisation: everything up to pdl_wait() below (index
+    // math, staging the logits tile, the column tables) overlaps the finalisation kernel; the
+    // upstream gradient, the weights, the statistics cache and dL/dlogits are touched only after it.
+    float go = 0.f, coef_ms = 0.f;
+    bool dep_ready = false;
+    const int Cd = PAD ? g.C : CT;                           // exact instantiations: constant divisor
+    const float4* __restrict__ ax = (const float4*)aux;
+
+    // units < 2^31 (checked on the host): 32-bit divisions only
+    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
+    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
+    int coef_img = -1;
+    while (u < u_end) {
+        const unsigned col = u / (unsigned)g.H;
+        const int ys = (int)(u - col * (unsigned)g.H);
+        const int ye = (int)min((unsigned)g.H, (unsigned)ys + (u_end - u));
+        u += (unsigned)(ye - ys);
+        const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
+        __syncthreads();                                     // previous segment done with all shared arrays
+        load_tile(s_tile, lo, g, sp);
+        if (!dep_ready) {
+            pdl_wait();
+            go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
+            if (GUIDE) coef_ms = (float)((double)go / (double)(*nvalid));      // mean over the valid pixels
+            else coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
+            dep_ready = true;
+        }
+        if (IW && sp.n != coef_img) {
+            if (tid < g.C)
+                s_coef[tid] = (float)(-2.0 * (double)weights[sp.n * g.C + tid] * (double)go /
+                                      ((double)n_norm * (double)g.C));
+            coef_img = sp.n;
+        }
+
+        const bool active = (sp.xs + tid) < sp.xe;
+        const int x = active ? sp.xs + tid : sp.xe - 1;
+        int x0, x1;
+        float lx0, lx1;
+        src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
+        const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
+        s_lx0[tid] = lx0;
+        s_lx1[tid] = lx1;
+        s_j0[tid] = active ? j0 : -1;
+        s_j1[tid] = active ? j1 : -1;
+        for (int i = tid; i < 4 * g.ncp; i += kTW) s_rng[i] = 0;
+        if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
+        __syncthreads();
+        if (active) {
+            const bool last = (sp.xs + tid + 1 == sp.xe);
+            if (tid == 0 || s_j0[tid - 1] != j0) s_rng[0 * g.ncp + j0] = tid;
+            if (last || s_j0[tid + 1] != j0) s_rng[1 * g.ncp + j0] = tid + 1;
+            if (tid == 0 || s_j1[tid - 1] != j1) s_rng[2 * g.ncp + j1] = tid;
+            if (last || s_j1[tid + 1] != j1) s_rng[3 * g.ncp + j1] = tid + 1;
+        }
+        __syncthreads();
+
+        constexpr int CP = (CT + 1) / 2;
+        float2 Ha[CP], Hb[CP], dHa[CP], dHb[CP];
+        int ra = -1, rb = -1;
+
+        // horizontal adjoint of one finished low-res row: every thread parks its d t_r[c] in
+        // shared memory, then one thread per (class, low-res column) gathers its <=2 runs
+        // of output columns and issues one red.global.add.
+        auto flush_row = [&](int r, const float2 (&dH)[CP]) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (!PAD || c < g.C) s_stage[c * (kTW + 1) + tid] = active ? lane_of(dH[c >> 1], c) : 0.f;
+            __syncthreads();
+            float* out = grad_lo + (((long long)sp.n * g.C) * g.h + r) * g.w + sp.c_lo;
+            const int cells = Cd * sp.nc;
+            for (int idx = tid; idx < cells; idx += kTW) {
+                const int j = idx / Cd, c = idx - j * Cd;
+                const float* colp = s_stage + c * (kTW + 1);
+                float acc = 0.f;
+                for (int t = s_rng[j], te = s_rng[g.ncp + j]; t < te; ++t) acc = fmaf(s_lx0[t], colp[t], acc);
+                for (int t = s_rng[2 * g.ncp + j], te = s_rng[3 * g.ncp + j]; t < te; ++t) acc = fmaf(s_lx1[t], colp[t], acc);
+                atomicAdd(out + (long long)c * g.h * g.w + j, acc);
+            }
+            __syncthreads();
+        };
+
+        // cached statistics of the next row are fetched while the current row is computed
+        const float4* axp = CACHED ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
+        float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CACHED) nx = __ldg(axp);
+        for (int y = sp.ys; y < sp.ye; ++y) {
+            int y0, y1;
+            float ly0, ly1;
+            row_params(s_rows, g, use_tab, sp.ys, y, y0, y1, ly0, ly1);
+            const float c_m = nx.x, c_qs = nx.y, c_is2 = nx.z;
+            const float nx_prev_z = nx.z;                    // GUIDE: label_2 bits
+            const int c_k = __float_as_int(nx.w);
+            if (CACHED && y + 1 < sp.ye) { axp += g.W; nx = __ldg(axp); }
+            if (y0 != ra) {
+                if (ra >= 0) flush_row(ra, dHa);
+                if (y0 == rb) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) { Ha[p] = Hb[p]; dHa[p] = dHb[p]; }
+                } else {
+                    if (rb >= 0) flush_row(rb, dHb);
+                    hline<CT, PAD>(Ha, s_tile, g, y0 - sp.r_lo, j0, j1, lx0, lx1);
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) dHa[p] = make_float2(0.f, 0.f);
+                }
+                ra = y0;
+                rb = -1;
+            }
+            if (y1 != rb) {
+                if (rb >= 0) flush_row(rb, dHb);
+                if (y1 == ra) {
+#pragma unroll
+                    for (int p = 0; p < CP; ++p) Hb[p] = Ha[p];
+                } else {
+                    hline<CT, PAD>(Hb, s_tile, g, y1 - sp.r_lo, j0, j1, lx0, lx1);
+                }
+#pragma unroll
+                for (int p = 0; p < CP; ++p) dHb[p] = make_float2(0.f, 0.f);
+                rb = y1;
+            }
+            // g_c = a p_c (p_c - q) = (a / s^2) e_c (e_c - q s)
+            const float2 w0 = splat(ly0), w1 = splat(ly1);
+            if (CACHED && GUIDE) {
+                // cache = {m, 1/s, label_2}: p_c = e_c / s, g_c = coef * (p_c - onehot(label_2))
+                const int lab = __float_as_int(nx_prev_z);
+                const float a = (lab >= 0) ? coef_ms : 0.f;
+                const float labf = (float)lab;
+                const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), is = splat(c_qs);
+                const float2 l2e = splat(kLog2e), nm = splat(-c_m * kLog2e);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) {
+                    const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+                    const float2 t = __ffma2_rn(zp, l2e, nm);
+                    const float2 ep = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    const float2 noh = make_float2(labf == (float)(2 * p) ? -1.f : 0.f, labf == (float)(2 * p + 1) ? -1.f : 0.f);
+                    const float2 v = __ffma2_rn(ep, is, noh);
+                    dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                    dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                }
+            } else if (CACHED) {
+                // max, q*s, 1/s^2 and the argmax class come from the forward's cache: no reduction over
+                // the classes is left, so every class pair streams straight into the accumulators
+                const float a = (IW ? s_coef[c_k] : coef_ms) * c_is2;
+                const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nqs = splat(-c_qs);
+                const float2 l2e = splat(kLog2e), nm = splat(-c_m * kLog2e);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) {
+                    const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+                    const float2 t = __ffma2_rn(zp, l2e, nm);
+                    const float2 ep = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    const float2 v = __fmul2_rn(ep, __fadd2_rn(ep, nqs));
+                    dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                    dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                }
+            } else {
+                float2 z[CP], e[CP];
+#pragma unroll
+                for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+                float m, inv_s, q, qs;
+                const int k = pixel_stats<CT, IW>(z, e, m, inv_s, q, qs);
+                const float a = (IW ? s_coef[k] : coef_ms) * inv_s * inv_s;
+                const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nqs = splat(-qs);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) {
+                    const float2 v = __fmul2_rn(e[p], __fadd2_rn(e[p], nqs));
+                    dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                    dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                }
+            }
+        }
+        if (ra >= 0) flush_row(ra, dHa);
+        if (rb >= 0) flush_row(rb, dHb);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+extern int g_fused_rows;   // tuning knob (fused_loss.cu): 0 = automatic (one balanced wave), R = about R rows per CTA
+
+static inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
+    }
+    return n;
+}
+
+struct Plan {
+    FusedGeo g;
+    long long units;
+    int grid;
+};
+
+// geometry + grid for `ctas_per_sm` co-resident CTAs per SM
+static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_per_sm, Plan& p) {
+    if (H < h || W < w || H > 65535) return MSQ_E_GEOMETRY;
+    FusedGeo& g = p.g;
+    g.C = C; g.h = h; g.w = w; g.H = H; g.W = W;
+    g.sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    g.sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const int tiles_x = (W + kTW - 1) / kTW;
+    p.units = (long long)n * tiles_x * H;
+    if (p.units >= (1LL << 31)) return MSQ_E_GEOMETRY;
+    long long grid = (long long)sm_count() * ctas_per_sm;
+    if (g_fused_rows > 0) grid = (p.units + g_fused_rows - 1) / g_fused_rows;
+    else if (p.units / grid < 4) grid = p.units / 4;          // tiny problems: at least 4 rows per CTA
+    if (grid < 1) grid = 1;
+    if (grid > p.units) grid = p.units;
+    p.grid = (int)grid;
+    long long rmax = (p.units + grid - 1) / grid;
+    if (rmax > H) rmax = H;
+    g.R = (int)rmax;
+    int nrm = (int)ceilf(g.sy * (float)(rmax - 1)) + 3;
+    int ncp = (int)ceilf(g.sx * (float)(kTW - 1)) + 3;
+    if (nrm > h) nrm = h;
+    if (ncp > w) ncp = w;
+    g.nrm = nrm;
+    g.ncp = ncp | 1;       // odd pitch: consecutive tile rows start in different banks
+    return 0;
+}
+
+template <typename K>
+static int occupancy(K kernel, size_t smem, int fallback) {
+    int occ = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTW, smem) != cudaSuccess || occ < 1) occ = fallback;
+    return occ;
+}
+
+static inline size_t row_tab_bytes(const FusedGeo& g) { return g.R <= kRowTabMax ? (size_t)g.R * 16 : 0; }
+static inline size_t fwd_smem(const FusedGeo& g, bool iw) {
+    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + (size_t)g.C * g.nrm * g.ncp * sizeof(float);
+}
+static inline size_t bwd_smem(const FusedGeo& g) {
+    return row_tab_bytes(g) + ((size_t)g.C * g.nrm * g.ncp + (size_t)g.C * (kTW + 1) + 2 * kTW) * sizeof(float) +
+           (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int);
+}
+
+
+}  // namespace msq

@@ -148,7 +148,7 @@ class _FusedLoss(torch.autograd.Function):
         accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
         out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
         aux = grad = None
-        if logits.requires_grad and torch.is_grad_enabled() and USE_STATS_CACHE:
+        if ctx.needs_input_grad[0] and USE_STATS_CACHE:      # (grad mode is always off inside forward)
             aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device=lo.device)
             grad = torch.empty_like(lo)
         _lib.check(lib.msq_fused_fwd(

@@ -71,3 +71,10 @@ def eval_pair_np(shape, c, seed):
     gt = rng.integers(-1, c, shape)
     pr = rng.integers(0, c, shape)
     return gt, pr
+
+
+def second_head(head1, seed, noise=0.5):
+    """Logits of the other classifier head for the multi-level guidance cases (cfg 3):
+    ``head1 + noise * randn`` -- correlated with head 1, as two heads of one network are."""
+    g = torch.Generator().manual_seed(int(seed) + 104729)
+    return (head1 + noise * torch.randn(head1.shape, generator=g)).contiguous()

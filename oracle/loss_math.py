@@ -111,3 +111,31 @@ def near_tie_pixels(z32: np.ndarray, ulps: int = 16) -> np.ndarray:
     s = np.sort(z32, axis=1)
     top, second = s[:, -1], s[:, -2]
     return (top - second) <= ulps * np.spacing(np.abs(top).astype(np.float32))
+
+
+def guidance(lo1_32: np.ndarray, lo2_32: np.ndarray, out_hw, threshold: float, grad_scale: float = 1.0):
+    """Closed form of the multi-level guidance term (``tools/solve_gta5.py:206-213``) in float64:
+    label_2 from the fp32 softmaxes exactly as torch computes them, CE and its gradient w.r.t. the
+    head-2 low-resolution logits without autograd:
+        loss2      = mean over valid px of -log p2[label_2]
+        dloss2/dz2 = (p2 - onehot(label_2)) / n_valid  on valid px, 0 elsewhere."""
+    z1 = bilinear.upsample(lo1_32, out_hw)
+    z2 = bilinear.upsample(lo2_32, out_hw)
+    p1 = F.softmax(torch.from_numpy(z1), dim=1)
+    p2 = F.softmax(torch.from_numpy(z2), dim=1)
+    keep = (torch.max(p1, 1)[0] > threshold) | (torch.max(p2, 1)[0] > threshold)
+    lab = torch.where(keep, torch.max((p1 + p2) / 2, 1)[1], torch.full((1,), -1, dtype=torch.long)).numpy()
+    valid = lab >= 0
+    nvalid = int(valid.sum())
+    p64 = softmax64(z2)
+    z64 = z2.astype(np.float64)
+    lse = np.log(np.exp(z64 - z64.max(axis=1, keepdims=True)).sum(axis=1)) + z64.max(axis=1)
+    sel = np.take_along_axis(z64, np.maximum(lab, 0)[:, None], axis=1)[:, 0]
+    with np.errstate(all='ignore'):
+        loss2 = np.float64((lse - sel)[valid].sum()) / nvalid if nvalid else np.float64('nan')
+        onehot = np.zeros_like(p64)
+        np.put_along_axis(onehot, np.maximum(lab, 0)[:, None], 1.0, axis=1)
+        # torch: with zero valid pixels the loss is NaN (0/0) but nll_loss_backward yields zeros
+        gz = (p64 - onehot) * valid[:, None] * (grad_scale / nvalid if nvalid else 0.0)
+    return dict(label_2=lab, nvalid=nvalid, loss2=loss2, grad_logits2=bilinear.upsample_adjoint(gz, lo2_32.shape[2:]),
+                z1=z1, z2=z2)

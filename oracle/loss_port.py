@@ -105,3 +105,26 @@ def multi_level_guidance(pred: torch.Tensor, pred_2: torch.Tensor, threshold: fl
     label_2 = torch.where(keep, arg_c, torch.ones(1).to(pred.device, dtype=torch.long) * ignore_index)
     loss_2 = F.cross_entropy(pred_2, label_2, ignore_index=ignore_index)
     return label_2, loss_2
+
+
+def chain_multi(lo1: torch.Tensor, lo2: torch.Tensor, out_hw, num_class: int, kind: str = "iw",
+                ratio: float = 0.2, threshold: float = 0.95, lambda_target: float = 0.1,
+                lambda_seg: float = 0.1):
+    """The whole ``--multi`` target step (``tools/solve_gta5.py:178-218``) from the two heads'
+    low-resolution logits: both upsamples, both softmaxes, head-1 adaptation loss, guidance CE on
+    head 2, backward.  Returns dict(loss_target, loss_target_2, label_2, nvalid, grad1, grad2, hist)."""
+    x1 = lo1.detach().clone().requires_grad_(True)
+    x2 = lo2.detach().clone().requires_grad_(True)
+    pred, prob = prologue(x1, out_hw)
+    pred_2 = F.interpolate(x2, size=tuple(out_hw), mode='bilinear', align_corners=True)
+    hist = None
+    if kind == "iw":
+        loss1, hist, _ = iw_maxsquare(prob, num_class, ratio, return_aux=True)
+    else:
+        loss1 = maxsquare(prob)
+    loss_target = lambda_target * loss1
+    label_2, ce = multi_level_guidance(pred, pred_2, threshold)
+    loss_target_2 = lambda_seg * lambda_target * ce
+    (loss_target + loss_target_2).backward()
+    return dict(loss_target=loss_target.detach(), loss_target_2=loss_target_2.detach(), label_2=label_2,
+                nvalid=int((label_2 >= 0).sum()), grad1=x1.grad, grad2=x2.grad, hist=hist)

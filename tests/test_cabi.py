@@ -32,7 +32,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.msq_abi_version() == 2
+    assert lib.msq_abi_version() == 3
     assert lib.msq_error_string(0) == b"success"
     for code in (-1, -2, -3, -4):
         assert lib.msq_error_string(code).startswith(b"msq:")
@@ -46,10 +46,10 @@ def test_state_layout(lib):
         assert lay.accum_bytes % 16 == 0 and lay.out_bytes % 16 == 0
         assert lay.sumsq_off % 8 == 0 and lay.kept_off % 8 == 0 and lay.hist_off % 4 == 0
         assert lay.hist_off >= lay.sumsq_off + 8 * nc
-        assert lay.accum_bytes >= lay.ticket_off + 4
+        assert lay.accum_bytes >= lay.nvalid_off + 8 * 16 and lay.ce_off % 8 == 0
         assert lay.loss_off % 4 == 0 and lay.weights_off % 4 == 0 and lay.sum_out_off % 8 == 0
         assert lay.stats_off % 8 == 0 and lay.stats_off >= lay.hist_out_off + 4 * nc
-        assert lay.out_bytes >= lay.stats_off + 8 * (1 + c)
+        assert lay.out_bytes >= lay.loss2_off + 4 and lay.nvalid_out_off % 8 == 0
     bad = _lib.StateLayout()
     assert lib.msq_state_layout_get(1, 33, ctypes.byref(bad)) == -1
     assert lib.msq_state_layout_get(0, 19, ctypes.byref(bad)) == -1

@@ -16,7 +16,8 @@ def msq():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     import maxsquareloss_b200 as m
-    from maxsquareloss_b200 import _lib
+    from maxsquareloss_b200 import _lib, build
+    build.build()        # no-op when the in-tree library is current
     _lib.load()          # fail loudly if the extension is missing
     return m
 
