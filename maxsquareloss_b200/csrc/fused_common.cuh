@@ -2,12 +2,14 @@
 // staging, per-pixel softmax statistics, the forward / backward column-walk kernels and the
 // host-side launch planning.
 #pragma once
+#include <mutex>
 #include "common.cuh"
 
 
 namespace msq {
 
 constexpr int kTW = 128;                        // output columns (= threads) per CTA
+constexpr int kRun = 8;                         // backward fast path: output columns per low-res cell and tap side
 #ifndef MSQ_FWD_MINB
 #define MSQ_FWD_MINB 4                          // co-resident CTAs per SM the forward is compiled for
 #endif
@@ -41,6 +43,7 @@ struct FusedGeo {
     int C, h, w, H, W;
     float sy, sx;        // (in-1)/(out-1) in fp32 (0 when out == 1)
     int R;               // output rows per strip
+    int fastx;           // every run of output columns sharing x0 (or x1) within a tile is <= kRun long
     int nrm, ncp;        // max low-res rows / cols any strip touches (tile pitch)
 };
 
@@ -167,21 +170,42 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// Stage the low-res tile [C][nr][nc] (pitches nrm, ncp) in shared memory with
+// Class pitch of the shared-memory tile: the tile is stored channel-LAST, [row][col][cpd(CT)],
+// so that the C logits of one low-res cell are contiguous and a thread fetches them with
+// cpd/4 LDS.128 instead of C scalar loads with C address computations.
+__host__ __device__ constexpr int cpd(int ct) { return (ct + 3) / 4 * 4; }
+
+// Lanes c >= C of every cell (padded class counts, and the odd lane of an odd C) hold
+// kPadLogit for the whole kernel: written once here, never touched by load_tile.
+template <int CT>
+__device__ __forceinline__ void init_tile_pad(float* s_tile, const FusedGeo& g) {
+    constexpr int CPD = cpd(CT);
+    const int cells = g.nrm * g.ncp;
+    const int npad = CPD - g.C;
+    if (npad <= 0) return;
+    for (int i = threadIdx.x; i < cells * npad; i += kTW) {
+        const int cell = i / npad, k = i - cell * npad;
+        s_tile[cell * CPD + g.C + k] = kPadLogit;
+    }
+}
+
+// Stage the low-res tile [nr][nc][CPD] (row pitch ncp cells) in shared memory with
 // cp.async (LDGSTS): every element is in flight at once, no register staging.
-// Thread t owns tile element (t / nc, t % nc) of every class: one integer division per
-// segment, then one cp.async per class.
+// Thread t owns tile cell (t / nc, t % nc): one integer division per segment, then one
+// cp.async per class (global reads coalesced along the row across threads).
+template <int CT>
 __device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict__ lo, const FusedGeo& g,
                                           const Strip& s) {
+    constexpr int CPD = cpd(CT);
     const int cells = s.nr * s.nc;
-    const int hw = g.h * g.w, cstride = g.nrm * g.ncp;
+    const int hw = g.h * g.w;
     const float* base = lo + ((long long)s.n * g.C * g.h + s.r_lo) * g.w + s.c_lo;
     for (int t = threadIdx.x; t < cells; t += kTW) {
         const int r = t / s.nc, j = t - r * s.nc;
         const float* src = base + r * g.w + j;
-        float* dst = s_tile + r * g.ncp + j;
+        float* dst = s_tile + (r * g.ncp + j) * CPD;
 #pragma unroll 4
-        for (int c = 0; c < g.C; ++c) cp_async4(dst + c * cstride, src + (long long)c * hw);
+        for (int c = 0; c < g.C; ++c) cp_async4(dst + c, src + (long long)c * hw);
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -190,18 +214,15 @@ __device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict
 template <int CT, bool PAD>
 __device__ __forceinline__ void hline(float2 (&Hx)[(CT + 1) / 2], const float* s_tile, const FusedGeo& g, int rr,
                                       int j0, int j1, float lx0, float lx1) {
-    constexpr int CP = (CT + 1) / 2;
-    const float* row = s_tile + rr * g.ncp;
-    const int cstride = g.nrm * g.ncp;
+    constexpr int CP = (CT + 1) / 2, CPD = cpd(CT);
+    const float4* c0 = reinterpret_cast<const float4*>(s_tile + (rr * g.ncp + j0) * CPD);
+    const float4* c1 = reinterpret_cast<const float4*>(s_tile + (rr * g.ncp + j1) * CPD);
     const float2 l0 = splat(lx0), l1 = splat(lx1);
 #pragma unroll
-    for (int p = 0; p < CP; ++p) {
-        const int c0 = 2 * p, c1 = 2 * p + 1;
-        const bool in0 = !PAD || c0 < g.C;
-        const bool in1 = (c1 < CT) && (!PAD || c1 < g.C);
-        const float2 a = make_float2(in0 ? row[c0 * cstride + j0] : kPadLogit, in1 ? row[c1 * cstride + j0] : kPadLogit);
-        const float2 b = make_float2(in0 ? row[c0 * cstride + j1] : kPadLogit, in1 ? row[c1 * cstride + j1] : kPadLogit);
-        Hx[p] = __ffma2_rn(a, l0, __fmul2_rn(b, l1));
+    for (int q = 0; q < CPD / 4; ++q) {
+        const float4 a = c0[q], b = c1[q];
+        Hx[2 * q] = __ffma2_rn(make_float2(a.x, a.y), l0, __fmul2_rn(make_float2(b.x, b.y), l1));
+        if (2 * q + 1 < CP) Hx[2 * q + 1] = __ffma2_rn(make_float2(a.z, a.w), l0, __fmul2_rn(make_float2(b.z, b.w), l1));
     }
 }
 
@@ -243,7 +264,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     unsigned long long* s_bkt = (unsigned long long*)s_raw;                   // [C][kTW]   (IW only)
     const bool use_tab = g.R <= kRowTabMax;
     float4* s_rows = (float4*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));    // [min(R, kRowTabMax)]
-    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));                   // [C][nrm][ncp]
+    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));                   // [nrm][ncp][cpd(CT)]
     __shared__ unsigned s_lab[MSQ_MAX_CLASSES];                               // label= histogram
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
@@ -253,6 +274,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
     }
     if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
+    init_tile_pad<CT>(s_tile, g);
     if (zero_buf) {                                    // zero dL/dlogits for the backward's red.adds: no memset launch
         const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
         const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
@@ -273,7 +295,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();                                   // previous segment done with s_tile / buckets zeroed
-        load_tile(s_tile, lo, g, sp);
+        load_tile<CT>(s_tile, lo, g, sp);
         if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
         __syncthreads();
 
@@ -287,6 +309,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         constexpr int CP = (CT + 1) / 2;
         float2 Ha[CP], Hb[CP];
         int ra = -1, rb = -1;
+        float4* axp = aux ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
         int run_k = -1;
         unsigned run_cnt = 0u;
         float run_q = 0.f;
@@ -333,7 +356,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             float m, inv_s, q, qs;
             const int k = pixel_stats<CT, IW>(z, e, m, inv_s, q, qs);
             if (active) {
-                if (aux) ax[((long long)sp.n * g.H + y) * g.W + x] = make_float4(m, qs, inv_s * inv_s, __int_as_float(k));
+                if (aux) axp[(long long)(y - sp.ys) * g.W] = make_float4(m, qs, inv_s * inv_s, __int_as_float(k));
                 if (IW) {
                     if (HAS_LABEL) {
                         const long long lv = label[((long long)sp.n * g.H + y) * g.W + x];
@@ -348,8 +371,10 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         }
         flush();
 
+        const int next_n = (u < u_end) ? (int)((u / (unsigned)g.H) / TX) : -1;
         if (IW) {
-            // reduce the private buckets of this segment: warp w owns classes w, w+4, ...
+            // reduce the private buckets when the CTA is done with this image: warp w owns classes w, w+4, ...
+            if (next_n == sp.n) continue;
             __syncthreads();
             for (int c = wid; c < g.C; c += kTW / 32) {
                 unsigned cnt = 0u;
@@ -372,7 +397,6 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             }
         } else {
             // MaxSquare: hand the running sum over when the next segment belongs to another image
-            const int next_n = (u < u_end) ? (int)((u / (unsigned)g.H) / TX) : -1;
             if (next_n != sp.n) {
                 ms_acc = warp_sum_u64(ms_acc);
                 if (lane == 0 && ms_acc) atomicAdd(&st.sumsq[rep_off + sp.n * g.C], ms_acc);
@@ -396,18 +420,23 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                  float* __restrict__ grad_lo, const void* __restrict__ aux,
                  const unsigned long long* __restrict__ nvalid = nullptr) {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    constexpr int CP = (CT + 1) / 2, CPD = cpd(CT), SP = CPD + 2;     // SP: stage pitch (floats), 8 B aligned rows
     const bool use_tab = g.R <= kRowTabMax;
     float4* s_rows = (float4*)s_raw;                         // [min(R, kRowTabMax)]
-    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));  // [C][nrm][ncp]
-    float* s_stage = s_tile + g.C * g.nrm * g.ncp;           // [C][kTW+1]
-    float* s_lx0 = s_stage + g.C * (kTW + 1);                // [kTW]
+    float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));  // [nrm][ncp][CPD]
+    float* s_stage = s_tile + CPD * g.nrm * g.ncp;           // [kTW + kRun][SP]: d t_r[c] of every column, class-innermost
+    float* s_wt = s_stage + (kTW + kRun) * SP;               // [ncp][2 kRun]: horizontal weights of each cell's taps
+    float* s_lx0 = s_wt + g.ncp * 2 * kRun;                  // [kTW]
     float* s_lx1 = s_lx0 + kTW;                              // [kTW]
     int* s_j0 = (int*)(s_lx1 + kTW);                         // [kTW]
     int* s_j1 = s_j0 + kTW;                                  // [kTW]
     int* s_rng = s_j1 + kTW;                                 // [4][ncp]: start0,end0,start1,end1
     __shared__ float s_coef[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x;
+    const bool fastx = g.fastx != 0;
     pdl_trigger();
+    init_tile_pad<CT>(s_tile, g);
+    for (int i = tid; i < kRun * SP; i += kTW) s_stage[kTW * SP + i] = 0.f;      // rows past the tile: zero taps
     // Launched with programmatic stream serialisation: everything up to pdl_wait() below (index
     // math, staging the logits tile, the column tables) overlaps the finalisation kernel; the
     // upstream gradient, the weights, the statistics cache and dL/dlogits are touched only after it.
@@ -428,7 +457,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();                                     // previous segment done with all shared arrays
-        load_tile(s_tile, lo, g, sp);
+        load_tile<CT>(s_tile, lo, g, sp);
         if (!dep_ready) {
             pdl_wait();
             go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
@@ -454,6 +483,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         s_j0[tid] = active ? j0 : -1;
         s_j1[tid] = active ? j1 : -1;
         for (int i = tid; i < 4 * g.ncp; i += kTW) s_rng[i] = 0;
+        if (fastx) for (int i = tid; i < 2 * kRun * g.ncp; i += kTW) s_wt[i] = 0.f;
         if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
         __syncthreads();
         if (active) {
@@ -464,28 +494,60 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             if (last || s_j1[tid + 1] != j1) s_rng[3 * g.ncp + j1] = tid + 1;
         }
         __syncthreads();
+        if (fastx && active) {        // tap k of cell j: column s_rng[j] + k with weight lx (runs are <= kRun long: host-checked)
+            const int k0 = tid - s_rng[j0], k1 = tid - s_rng[2 * g.ncp + j1];
+            if (k0 < kRun) s_wt[j0 * 2 * kRun + k0] = lx0;
+            if (k1 < kRun) s_wt[j1 * 2 * kRun + kRun + k1] = lx1;
+        }
 
-        constexpr int CP = (CT + 1) / 2;
         float2 Ha[CP], Hb[CP], dHa[CP], dHb[CP];
         int ra = -1, rb = -1;
 
         // horizontal adjoint of one finished low-res row: every thread parks its d t_r[c] in
-        // shared memory, then one thread per (class, low-res column) gathers its <=2 runs
-        // of output columns and issues one red.global.add.
+        // shared memory (class-innermost), then one thread per (low-res column, class pair)
+        // gathers the <= 2 kRun taps of its cell with packed FMAs and issues the red.global.adds.
         auto flush_row = [&](int r, const float2 (&dH)[CP]) {
+            float2* mine = reinterpret_cast<float2*>(s_stage + tid * SP);
 #pragma unroll
-            for (int c = 0; c < CT; ++c)
-                if (!PAD || c < g.C) s_stage[c * (kTW + 1) + tid] = active ? lane_of(dH[c >> 1], c) : 0.f;
+            for (int p = 0; p < CP; ++p) mine[p] = active ? dH[p] : make_float2(0.f, 0.f);
             __syncthreads();
             float* out = grad_lo + (((long long)sp.n * g.C) * g.h + r) * g.w + sp.c_lo;
-            const int cells = Cd * sp.nc;
-            for (int idx = tid; idx < cells; idx += kTW) {
-                const int j = idx / Cd, c = idx - j * Cd;
-                const float* colp = s_stage + c * (kTW + 1);
-                float acc = 0.f;
-                for (int t = s_rng[j], te = s_rng[g.ncp + j]; t < te; ++t) acc = fmaf(s_lx0[t], colp[t], acc);
-                for (int t = s_rng[2 * g.ncp + j], te = s_rng[3 * g.ncp + j]; t < te; ++t) acc = fmaf(s_lx1[t], colp[t], acc);
-                atomicAdd(out + (long long)c * g.h * g.w + j, acc);
+            const long long hw = (long long)g.h * g.w;
+            if (fastx) {
+                const int items = sp.nc * CP;
+                for (int idx = tid; idx < items; idx += kTW) {
+                    const int j = idx / CP, p = idx - j * CP;
+                    const float4* wv = reinterpret_cast<const float4*>(s_wt + j * 2 * kRun);
+                    const float2* a = reinterpret_cast<const float2*>(s_stage + s_rng[j] * SP) + p;
+                    const float2* b = reinterpret_cast<const float2*>(s_stage + s_rng[2 * g.ncp + j] * SP) + p;
+                    float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+                    for (int q = 0; q < kRun / 4; ++q) {
+                        const float4 w0 = wv[q], w1 = wv[kRun / 4 + q];
+                        acc0 = __ffma2_rn(splat(w0.x), a[(4 * q + 0) * (SP / 2)], acc0);
+                        acc1 = __ffma2_rn(splat(w1.x), b[(4 * q + 0) * (SP / 2)], acc1);
+                        acc0 = __ffma2_rn(splat(w0.y), a[(4 * q + 1) * (SP / 2)], acc0);
+                        acc1 = __ffma2_rn(splat(w1.y), b[(4 * q + 1) * (SP / 2)], acc1);
+                        acc0 = __ffma2_rn(splat(w0.z), a[(4 * q + 2) * (SP / 2)], acc0);
+                        acc1 = __ffma2_rn(splat(w1.z), b[(4 * q + 2) * (SP / 2)], acc1);
+                        acc0 = __ffma2_rn(splat(w0.w), a[(4 * q + 3) * (SP / 2)], acc0);
+                        acc1 = __ffma2_rn(splat(w1.w), b[(4 * q + 3) * (SP / 2)], acc1);
+                    }
+                    const float2 acc = __fadd2_rn(acc0, acc1);
+                    const int c0 = 2 * p;
+                    if (!PAD || c0 < g.C) atomicAdd(out + (long long)c0 * hw + j, acc.x);
+                    if (c0 + 1 < CT && (!PAD || c0 + 1 < g.C)) atomicAdd(out + (long long)(c0 + 1) * hw + j, acc.y);
+                }
+            } else {
+                const int cells = Cd * sp.nc;
+                for (int idx = tid; idx < cells; idx += kTW) {
+                    const int j = idx / Cd, c = idx - j * Cd;
+                    const float* colp = s_stage + c;
+                    float acc = 0.f;
+                    for (int t = s_rng[j], te = s_rng[g.ncp + j]; t < te; ++t) acc = fmaf(s_lx0[t], colp[t * SP], acc);
+                    for (int t = s_rng[2 * g.ncp + j], te = s_rng[3 * g.ncp + j]; t < te; ++t) acc = fmaf(s_lx1[t], colp[t * SP], acc);
+                    atomicAdd(out + (long long)c * hw + j, acc);
+                }
             }
             __syncthreads();
         };
@@ -602,6 +664,24 @@ struct Plan {
     int grid;
 };
 
+// longest run of output columns, within one kTW-wide tile, that share the same left (x0) or
+// right (x1) low-res column: the backward's fast horizontal adjoint handles runs <= kRun
+static inline int max_column_run(int w, int W, float sx) {
+    int best = 0, run0 = 0, run1 = 0, p0 = -1, p1 = -1;
+    for (int x = 0; x < W; ++x) {
+        int x0, x1;
+        float l0, l1;
+        src_index(sx, x, w, x0, x1, l0, l1);
+        if (x % kTW == 0) { p0 = p1 = -1; }
+        run0 = (x0 == p0) ? run0 + 1 : 1;
+        run1 = (x1 == p1) ? run1 + 1 : 1;
+        p0 = x0; p1 = x1;
+        if (run0 > best) best = run0;
+        if (run1 > best) best = run1;
+    }
+    return best;
+}
+
 // geometry + grid for `ctas_per_sm` co-resident CTAs per SM
 static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_per_sm, Plan& p) {
     if (H < h || W < w || H > 65535) return MSQ_E_GEOMETRY;
@@ -609,6 +689,22 @@ static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_p
     g.C = C; g.h = h; g.w = w; g.H = H; g.W = W;
     g.sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
     g.sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    {   // the column-run scan is O(W): remember the last geometries (launches repeat them)
+        struct Key { int w, W, run; };
+        static Key cache[8];
+        static int used = 0, next = 0;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        int run = -1;
+        for (int i = 0; i < used; ++i) if (cache[i].w == w && cache[i].W == W) run = cache[i].run;
+        if (run < 0) {
+            run = max_column_run(w, W, g.sx);
+            cache[next] = Key{w, W, run};
+            next = (next + 1) % 8;
+            if (used < 8) ++used;
+        }
+        g.fastx = run <= kRun ? 1 : 0;
+    }
     const int tiles_x = (W + kTW - 1) / kTW;
     p.units = (long long)n * tiles_x * H;
     if (p.units >= (1LL << 31)) return MSQ_E_GEOMETRY;
@@ -626,7 +722,7 @@ static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_p
     if (nrm > h) nrm = h;
     if (ncp > w) ncp = w;
     g.nrm = nrm;
-    g.ncp = ncp | 1;       // odd pitch: consecutive tile rows start in different banks
+    g.ncp = ncp;
     return 0;
 }
 
@@ -639,11 +735,13 @@ static int occupancy(K kernel, size_t smem, int fallback) {
 }
 
 static inline size_t row_tab_bytes(const FusedGeo& g) { return g.R <= kRowTabMax ? (size_t)g.R * 16 : 0; }
-static inline size_t fwd_smem(const FusedGeo& g, bool iw) {
-    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + (size_t)g.C * g.nrm * g.ncp * sizeof(float);
+static inline size_t tile_bytes(const FusedGeo& g, int ct) { return (size_t)cpd(ct) * g.nrm * g.ncp * sizeof(float); }
+static inline size_t fwd_smem(const FusedGeo& g, bool iw, int ct) {
+    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + tile_bytes(g, ct);
 }
-static inline size_t bwd_smem(const FusedGeo& g) {
-    return row_tab_bytes(g) + ((size_t)g.C * g.nrm * g.ncp + (size_t)g.C * (kTW + 1) + 2 * kTW) * sizeof(float) +
+static inline size_t bwd_smem(const FusedGeo& g, int ct) {
+    return row_tab_bytes(g) + tile_bytes(g, ct) +
+           ((size_t)(kTW + kRun) * (cpd(ct) + 2) + (size_t)g.ncp * 2 * kRun + 2 * kTW) * sizeof(float) +
            (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int);
 }
 

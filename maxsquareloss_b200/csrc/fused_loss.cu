@@ -38,9 +38,9 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
         Plan p;                                                                                \
         int rc = make_plan(C, h, w, H, W, n, MSQ_FWD_MINB, p);                                            \
         if (rc) return rc;                                                                     \
-        const int occ = occupancy(K, fwd_smem(p.g, iw), 1);                                    \
+        const int occ = occupancy(K, fwd_smem(p.g, iw, CT), 1);                                    \
         if (occ != MSQ_FWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
-        const size_t smem = fwd_smem(p.g, iw);                                                 \
+        const size_t smem = fwd_smem(p.g, iw, CT);                                                 \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, label, st, aux, zero_buf, zero_count); \
@@ -66,9 +66,9 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
         Plan p;                                                                                \
         int rc = make_plan(C, h, w, H, W, n, MSQ_BWD_MINB, p);                                            \
         if (rc) return rc;                                                                     \
-        const int occ = occupancy(K, bwd_smem(p.g), 1);                                        \
+        const int occ = occupancy(K, bwd_smem(p.g, CT), 1);                                        \
         if (occ != MSQ_BWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
-        const size_t smem = bwd_smem(p.g);                                                     \
+        const size_t smem = bwd_smem(p.g, CT);                                                     \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         const cudaError_t le = launch_pdl(K, dim3(p.grid), dim3(kTW), smem, s, lo, p.g, n, (unsigned)p.units, nn,       \

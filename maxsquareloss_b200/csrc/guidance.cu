@@ -53,7 +53,7 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
     const bool use_tab = g.R <= kRowTabMax;
     float4* s_rows = (float4*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));
     float* s_tile1 = (float*)(s_rows + (use_tab ? g.R : 0));                  // [C][nrm][ncp]
-    float* s_tile2 = s_tile1 + g.C * g.nrm * g.ncp;
+    float* s_tile2 = s_tile1 + cpd(CT) * g.nrm * g.ncp;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rep = (int)(blockIdx.x % kRep), rep_off = rep * n_img * g.C;
     pdl_trigger();
@@ -69,6 +69,8 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
             if (zero2) zero2[i] = 0.f;
         }
     }
+    init_tile_pad<CT>(s_tile1, g);
+    init_tile_pad<CT>(s_tile2, g);
     float4* __restrict__ ax1 = (float4*)aux1;
     float4* __restrict__ ax2 = (float4*)aux2;
 
@@ -86,8 +88,8 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();
-        load_tile(s_tile1, lo1, g, sp);
-        load_tile(s_tile2, lo2, g, sp);
+        load_tile<CT>(s_tile1, lo1, g, sp);
+        load_tile<CT>(s_tile2, lo2, g, sp);
         if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
         __syncthreads();
 
@@ -258,8 +260,8 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(st.flags, kFlagNonFinite);
 }
 
-static inline size_t multi_smem(const FusedGeo& g, bool iw) {
-    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + 2 * (size_t)g.C * g.nrm * g.ncp * sizeof(float);
+static inline size_t multi_smem(const FusedGeo& g, bool iw, int ct) {
+    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + 2 * tile_bytes(g, ct);
 }
 
 template <int CT, bool PAD>
@@ -273,9 +275,9 @@ static int launch_multi_fwd(int mode, const float* lo1, const float* lo2, int C,
         Plan p;                                                                                \
         int rc = make_plan(C, h, w, H, W, n, 3, p);                                            \
         if (rc) return rc;                                                                     \
-        const int occ = occupancy(K, multi_smem(p.g, iw), 1);                                  \
+        const int occ = occupancy(K, multi_smem(p.g, iw, CT), 1);                                  \
         if (occ != 3) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
-        const size_t smem = multi_smem(p.g, iw);                                               \
+        const size_t smem = multi_smem(p.g, iw, CT);                                               \
         if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         K<<<p.grid, kTW, smem, s>>>(lo1, lo2, p.g, n, (unsigned)p.units, thr, st, aux1, aux2, zero1, zero2, zero_count, label_out); \
@@ -298,9 +300,9 @@ static int launch_guidance_bwd(const float* lo2, int C, int h, int w, int H, int
     Plan p;
     int rc = make_plan(C, h, w, H, W, n, MSQ_BWD_MINB, p);
     if (rc) return rc;
-    const int occ = occupancy(K, bwd_smem(p.g), 1);
+    const int occ = occupancy(K, bwd_smem(p.g, CT), 1);
     if (occ != MSQ_BWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }
-    const size_t smem = bwd_smem(p.g);
+    const size_t smem = bwd_smem(p.g, CT);
     if (smem > 200 * 1024) return MSQ_E_SMEM;
     if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const cudaError_t le = launch_pdl(K, dim3(p.grid), dim3(kTW), smem, s, lo2, p.g, n, (unsigned)p.units, n,
