@@ -15,83 +15,9 @@ namespace msq {
 __global__ void __launch_bounds__(256)
 finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_norm, unsigned long long kept_dense,
                 int multi) {
-    __shared__ double s_red[8];
-    __shared__ unsigned long long s_cls[MSQ_MAX_CLASSES];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
     pdl_trigger();          // the backward may start its prologue now
     pdl_wait();             // ... but this kernel needs every forward CTA's atomics
-    // thread 0's scalars are fetched first so that their latency overlaps everything else
-    unsigned long long kept_ld = 0ull;
-    unsigned flags_ld = 0u;
-    if (tid == 0) { kept_ld = *st.kept; flags_ld = *st.flags; }
-    // multi-level guidance: cross-entropy sum and valid-pixel count, one replica per lane of warp 0
-    unsigned long long ce_ld = 0ull, nv_ld = 0ull;
-    if (multi && tid < kRep) { ce_ld = st.ce[tid]; nv_ld = st.nvalid[tid]; st.ce[tid] = 0ull; st.nvalid[tid] = 0ull; }
-    if (tid < MSQ_MAX_CLASSES) s_cls[tid] = 0ull;
-    __syncthreads();
-    const int nc = n * C;
-    double part = 0.0;
-    unsigned long long cls_tot = 0ull;
-    for (int img = wid; img < n; img += nw) {
-        const int idx = img * C + lane;
-        unsigned hcnt = 0u;
-        unsigned long long sq = 0ull;
-        if (lane < C) {
-#pragma unroll
-            for (int r = 0; r < kRep; ++r) {          // independent loads: one latency
-                hcnt += st.hist[r * nc + idx];
-                sq += st.sumsq[r * nc + idx];
-            }
-#pragma unroll
-            for (int r = 0; r < kRep; ++r) { st.hist[r * nc + idx] = 0u; st.sumsq[r * nc + idx] = 0ull; }   // self-clean
-        }
-        const unsigned total = __reduce_add_sync(0xffffffffu, hcnt);
-        const double S = (double)sq * kInvFix;
-        float wgt = 1.0f;
-        if (mode == MSQ_MODE_IW && lane < C) wgt = iw_weight((float)hcnt, (float)total, r32, omr32);
-        if (lane < C) {
-            part += (double)wgt * S;
-            st.weights[idx] = wgt;
-            st.hist_out[idx] = (int)hcnt;
-            cls_tot += hcnt;
-        }
-        double simg = S;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) simg += __shfl_xor_sync(0xffffffffu, simg, o);
-        if (lane == 0) st.sum_out[img] = simg;
-    }
-    if (multi && wid == 0) {
-        ce_ld = warp_sum_u64(ce_ld);
-        nv_ld = warp_sum_u64(nv_ld);
-    }
-    if (lane < C && cls_tot) atomicAdd(&s_cls[lane], cls_tot);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_red[wid] = part;
-    __syncthreads();
-    if (tid < C) st.stats[1 + tid] = (double)s_cls[tid];
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int i = 0; i < nw; ++i) tot += s_red[i];
-        const unsigned long long kept_local = (kept_dense != 0ull) ? kept_dense : kept_ld;
-        const double scale = (double)n_norm / (double)n;
-        double loss;
-        if (mode == MSQ_MODE_IW) loss = -tot / ((double)n_norm * (double)C);
-        else loss = -tot / (2.0 * (double)kept_local * scale);
-        if (flags_ld & kFlagNonFinite) loss = __longlong_as_double(0x7ff8000000000000LL);
-        *st.loss = (float)loss;
-        *st.kept_out = kept_local;
-        st.stats[0] = loss;
-        if (multi) {       // nn.CrossEntropyLoss(ignore_index=-1): mean over the valid pixels, 0/0 = NaN as in torch
-            double l2 = ((double)ce_ld * kInvFix) / (double)nv_ld;
-            if (flags_ld & kFlagNonFinite) l2 = __longlong_as_double(0x7ff8000000000000LL);
-            *st.loss2 = (float)l2;
-            *st.nvalid_out = nv_ld;
-            *st.ce_out = (double)ce_ld * kInvFix;
-        }
-        *st.kept = 0ull;                       // self-clean
-        *st.flags = 0u;
-    }
+    finalize_body(st, mode, n, C, r32, omr32, n_norm, kept_dense, multi);
 }
 
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,

@@ -275,6 +275,9 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     }
     if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
     init_tile_pad<CT>(s_tile, g);
+    // launched with programmatic stream serialisation: the shared-memory set-up above overlaps the tail of
+    // whatever precedes this kernel in the stream; global memory is touched only from here on
+    pdl_wait();
     if (zero_buf) {                                    // zero dL/dlogits for the backward's red.adds: no memset launch
         const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
         const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
@@ -732,6 +735,53 @@ static int occupancy(K kernel, size_t smem, int fallback) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTW, smem) != cudaSuccess || occ < 1) occ = fallback;
     return occ;
+}
+
+// Launch plans are remembered per (kernel, geometry): the occupancy query, the shared-memory
+// opt-in and the column-run scan are done once, not on every launch (they cost more host time
+// than the launch itself, which matters for the host-buffer pipeline).
+struct LaunchPlan {
+    Plan p;
+    size_t smem;
+};
+struct PlanKey {
+    const void* kernel;
+    int C, h, w, H, W, n, rows;
+    bool operator==(const PlanKey& o) const {
+        return kernel == o.kernel && C == o.C && h == o.h && w == o.w && H == o.H && W == o.W && n == o.n && rows == o.rows;
+    }
+};
+static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
+    constexpr int kSlots = 32;
+    static PlanKey keys[kSlots];
+    static LaunchPlan vals[kSlots];
+    static int used = 0, next = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (put) {
+        keys[next] = key; vals[next] = lp;
+        next = (next + 1) % kSlots;
+        if (used < kSlots) ++used;
+        return true;
+    }
+    for (int i = 0; i < used; ++i) if (keys[i] == key) { lp = vals[i]; return true; }
+    return false;
+}
+
+// plan + shared-memory size for `kernel`, compiled for `minb` co-resident CTAs per SM
+template <typename K, typename SmemFn>
+static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp) {
+    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows};
+    if (plan_cache(key, lp, false)) return 0;
+    int rc = make_plan(C, h, w, H, W, n, minb, lp.p);
+    if (rc) return rc;
+    const int occ = occupancy(kernel, smem_of(lp.p.g), 1);
+    if (occ != minb) { rc = make_plan(C, h, w, H, W, n, occ, lp.p); if (rc) return rc; }
+    lp.smem = smem_of(lp.p.g);
+    if (lp.smem > 200 * 1024) return MSQ_E_SMEM;
+    if (lp.smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
+    plan_cache(key, lp, true);
+    return 0;
 }
 
 static inline size_t row_tab_bytes(const FusedGeo& g) { return g.R <= kRowTabMax ? (size_t)g.R * 16 : 0; }

@@ -35,15 +35,13 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
     const bool iw = mode != MSQ_MODE_MAXSQUARE;
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
-        Plan p;                                                                                \
-        int rc = make_plan(C, h, w, H, W, n, MSQ_FWD_MINB, p);                                            \
+        LaunchPlan lp;                                                                         \
+        const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_FWD_MINB,                          \
+                                   [&](const FusedGeo& g) { return fwd_smem(g, iw, CT); }, lp); \
         if (rc) return rc;                                                                     \
-        const int occ = occupancy(K, fwd_smem(p.g, iw, CT), 1);                                    \
-        if (occ != MSQ_FWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
-        const size_t smem = fwd_smem(p.g, iw, CT);                                                 \
-        if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<p.grid, kTW, smem, s>>>(lo, p.g, n, (unsigned)p.units, label, st, aux, zero_buf, zero_count); \
+        const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, (unsigned)lp.p.units, \
+                                          label, st, aux, zero_buf, zero_count);              \
+        if (le != cudaSuccess) return (int)le;                                                 \
     } while (0)
     if (!iw) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, false, false>));
     else if (label) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, true>));
@@ -63,15 +61,11 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
     }
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
-        Plan p;                                                                                \
-        int rc = make_plan(C, h, w, H, W, n, MSQ_BWD_MINB, p);                                            \
+        LaunchPlan lp;                                                                         \
+        const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_BWD_MINB,                          \
+                                   [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp);    \
         if (rc) return rc;                                                                     \
-        const int occ = occupancy(K, bwd_smem(p.g, CT), 1);                                        \
-        if (occ != MSQ_BWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
-        const size_t smem = bwd_smem(p.g, CT);                                                     \
-        if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        const cudaError_t le = launch_pdl(K, dim3(p.grid), dim3(kTW), smem, s, lo, p.g, n, (unsigned)p.units, nn,       \
+        const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, (unsigned)lp.p.units, nn, \
                                           (const float*)st.weights, grad_out, grad_out_value, grad_lo, aux,           \
                                           (const unsigned long long*)nullptr);                                       \
         if (le != cudaSuccess) return (int)le;                                                                        \

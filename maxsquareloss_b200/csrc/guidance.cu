@@ -61,6 +61,9 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
 #pragma unroll
         for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
     }
+    init_tile_pad<CT>(s_tile1, g);
+    init_tile_pad<CT>(s_tile2, g);
+    pdl_wait();            // global memory is touched only from here on (see fused_fwd_kernel)
     {
         const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
         const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
@@ -69,8 +72,6 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
             if (zero2) zero2[i] = 0.f;
         }
     }
-    init_tile_pad<CT>(s_tile1, g);
-    init_tile_pad<CT>(s_tile2, g);
     float4* __restrict__ ax1 = (float4*)aux1;
     float4* __restrict__ ax2 = (float4*)aux2;
 
@@ -272,15 +273,13 @@ static int launch_multi_fwd(int mode, const float* lo1, const float* lo2, int C,
     const unsigned zero_count = (zero1 || zero2) ? (unsigned)((size_t)n * C * h * w) : 0u;
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
-        Plan p;                                                                                \
-        int rc = make_plan(C, h, w, H, W, n, 3, p);                                            \
+        LaunchPlan lp;                                                                         \
+        const int rc = plan_launch(K, C, h, w, H, W, n, 3,                                     \
+                                   [&](const FusedGeo& g) { return multi_smem(g, iw, CT); }, lp); \
         if (rc) return rc;                                                                     \
-        const int occ = occupancy(K, multi_smem(p.g, iw, CT), 1);                                  \
-        if (occ != 3) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }         \
-        const size_t smem = multi_smem(p.g, iw, CT);                                               \
-        if (smem > 200 * 1024) return MSQ_E_SMEM;                                              \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        K<<<p.grid, kTW, smem, s>>>(lo1, lo2, p.g, n, (unsigned)p.units, thr, st, aux1, aux2, zero1, zero2, zero_count, label_out); \
+        const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo1, lo2, lp.p.g, n, (unsigned)lp.p.units, \
+                                          thr, st, aux1, aux2, zero1, zero2, zero_count, label_out); \
+        if (le != cudaSuccess) return (int)le;                                                 \
     } while (0)
     if (iw) MSQ_LAUNCH((multi_fwd_kernel<CT, PAD, true>));
     else MSQ_LAUNCH((multi_fwd_kernel<CT, PAD, false>));
@@ -297,15 +296,10 @@ static int launch_guidance_bwd(const float* lo2, int C, int h, int w, int H, int
         if (e != cudaSuccess) return (int)e;
     }
     auto K = fused_bwd_kernel<CT, PAD, false, true, true>;
-    Plan p;
-    int rc = make_plan(C, h, w, H, W, n, MSQ_BWD_MINB, p);
+    LaunchPlan lp;
+    const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_BWD_MINB, [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp);
     if (rc) return rc;
-    const int occ = occupancy(K, bwd_smem(p.g, CT), 1);
-    if (occ != MSQ_BWD_MINB) { rc = make_plan(C, h, w, H, W, n, occ, p); if (rc) return rc; }
-    const size_t smem = bwd_smem(p.g, CT);
-    if (smem > 200 * 1024) return MSQ_E_SMEM;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const cudaError_t le = launch_pdl(K, dim3(p.grid), dim3(kTW), smem, s, lo2, p.g, n, (unsigned)p.units, n,
+    const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo2, lp.p.g, n, (unsigned)lp.p.units, n,
                                       (const float*)st.weights, grad_out, 0.f, grad_lo, aux2,
                                       (const unsigned long long*)st.nvalid_out);
     if (le != cudaSuccess) return (int)le;
