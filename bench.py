@@ -298,10 +298,10 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- e2e (headline): C-ABI host-buffer pipeline (maxsquareloss_b200.HostPipeline -> msq_pipe_submit):
     #      every step copies its head logits from pinned HOST memory, runs fwd+bwd and copies the loss
-    #      and dL/dlogits back to the host; 3 steps in flight so copies overlap kernels.
+    #      and dL/dlogits back to the host; `depth` steps in flight so copies overlap kernels.
     e2e_pool = min(POOL, 16)
     host_in = [lo_pool[i].cpu().pin_memory() for i in range(e2e_pool)]
-    depth = 3
+    depth = int(os.environ.get("MSQ_BENCH_DEPTH", "8"))          # a step is ~100 us of latency end to end (H2D, kernels, D2H)
     pipe = msq.HostPipeline("iw", N_IMG, C, HW_LO, HW_OUT, ratio=RATIO, depth=depth)
     h_grad = [torch.empty(N_IMG, C, *HW_LO).pin_memory() for _ in range(depth)]
     h_loss = [torch.empty(()).pin_memory() for _ in range(depth)]
@@ -415,8 +415,8 @@ def run_b200(args, rank, world, local_rank):
                         "d2h_bytes_per_step": int(lo_bytes) + 4, "steps": e2e_steps,
                         "ms_per_step": e2e_s / e2e_steps * 1e3,
                         "how": "HostPipeline.submit -> C ABI msq_pipe_submit: per step pinned host logits H2D, fused "
-                               "fwd+bwd, loss + dL/dlogits D2H; 3 steps in flight, host waits on step i-3 before "
-                               "reusing its buffers", "last_loss": last_loss,
+                               f"fwd+bwd, loss + dL/dlogits D2H; {depth} steps in flight, host waits on step i-{depth} "
+                               "before reusing its buffers", "last_loss": last_loss,
                         "autograd_per_rank": {"value": ag_val, "unit": UNIT, "steps": ag_steps,
                                               "ms_per_step": ag_s / ag_steps * 1e3,
                                               "how": "IW_MaxSquareloss nn.Module + autograd, H2D/D2H and a stream sync "
