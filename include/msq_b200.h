@@ -179,6 +179,21 @@ int msq_guidance_bwd(const float* logits2, int n, int num_class, int h, int w, i
                      int grad_is_zeroed, msq_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Source-side step, fused from LOW-resolution head logits: nn.CrossEntropyLoss(ignore_index=-1)
+ * (tools/train_source.py:128,254,257) on the bilinearly upsampled logits, plus -- when cm != NULL --
+ * np.argmax + Eval.add_batch of the same tensors (tools/train_source.py:280-283, utils/eval.py:109-121).
+ *   label      int64 [N,out_h,out_w]; values outside [0,C) are ignored (the datasets emit -1)
+ *   out.loss2  the mean over the out.nvalid_out counted pixels (NaN if none); out.ce_out their sum
+ *   aux        float4-per-pixel cache (msq_fused_aux_bytes, nullable) consumed by msq_guidance_bwd,
+ *              which is this loss's backward: dL/dlogits = grad/n_valid * (softmax - onehot(label))
+ *   zero_grad  optional dL/dlogits buffer to zero-fill on the side
+ *   cm         optional uint64 [C*C] confusion matrix, ACCUMULATED (row = label, column = argmax)
+ * ------------------------------------------------------------------------- */
+int msq_source_ce_fwd(const float* logits, const int64_t* label, int n, int num_class, int h, int w,
+                      int out_h, int out_w, void* accum, void* out, void* aux /* nullable */,
+                      float* zero_grad /* nullable */, unsigned long long* cm /* nullable */, msq_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Evaluation: Eval.__generate_matrix / add_batch (utils/eval.py:109-121).
  *   cm      uint64 [C*C], row = ground truth, column = prediction, ACCUMULATED
  *   errs    uint32 [2], OR-ed: [0] a flattened index C*gt+pred was negative

@@ -78,3 +78,32 @@ def second_head(head1, seed, noise=0.5):
     ``head1 + noise * randn`` -- correlated with head 1, as two heads of one network are."""
     g = torch.Generator().manual_seed(int(seed) + 104729)
     return (head1 + noise * torch.randn(head1.shape, generator=g)).contiguous()
+
+
+def align_logits_to_labels(lo, labels, boost=4.0):
+    """Raise, in every low-resolution cell, the logit of the class the label map has at the cell's
+    position (nearest sample), so that argmax(upsampled logits) mostly equals the label -- a
+    prediction that looks like a trained network's (strong confusion-matrix diagonal)."""
+    n, c, h, w = lo.shape
+    H, W = labels.shape[-2:]
+    ys = torch.linspace(0, H - 1, h).round().long()
+    xs = torch.linspace(0, W - 1, w).round().long()
+    cell = labels[:, ys][:, :, xs]                                   # (n,h,w)
+    onehot = torch.zeros_like(lo)
+    onehot.scatter_(1, cell.clamp(min=0).unsqueeze(1), 1.0)
+    onehot = onehot * (cell >= 0).unsqueeze(1)
+    return (lo + boost * onehot).contiguous()
+
+
+def source_case(n, c, hw, HW, seed, scale, label_kind):
+    """(head logits, label map) of a source-side step case (tests/golden/source_kats.json)."""
+    lo = head_logits(n, c, hw, seed, scale)
+    if label_kind == "random":
+        y = random_labels(n, HW, c, seed)
+    elif label_kind == "ignored":
+        y = torch.full((n,) + tuple(HW), -1, dtype=torch.int64)
+    else:
+        y = blocky_labels(n, HW, c, seed, grid=(8, 16))
+    if label_kind == "aligned":
+        lo = align_logits_to_labels(lo, y)
+    return lo, y

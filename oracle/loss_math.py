@@ -139,3 +139,23 @@ def guidance(lo1_32: np.ndarray, lo2_32: np.ndarray, out_hw, threshold: float, g
         gz = (p64 - onehot) * valid[:, None] * (grad_scale / nvalid if nvalid else 0.0)
     return dict(label_2=lab, nvalid=nvalid, loss2=loss2, grad_logits2=bilinear.upsample_adjoint(gz, lo2_32.shape[2:]),
                 z1=z1, z2=z2)
+
+
+def source_ce(lo32: np.ndarray, target: np.ndarray, grad_scale: float = 1.0):
+    """Closed form (float64) of ``CrossEntropyLoss(ignore_index=-1)`` on the upsampled logits and of its
+    gradient w.r.t. the low-resolution logits; plus ``np.argmax`` of the fp32 upsampled logits."""
+    z = bilinear.upsample(lo32, target.shape[-2:])
+    z64 = z.astype(np.float64)
+    valid = (target >= 0) & (target < lo32.shape[1])
+    nvalid = int(valid.sum())
+    zmax = z64.max(axis=1)
+    lse = np.log(np.exp(z64 - zmax[:, None]).sum(axis=1)) + zmax
+    tgt = np.where(valid, target, 0)
+    sel = np.take_along_axis(z64, tgt[:, None], axis=1)[:, 0]
+    loss = np.float64((lse - sel)[valid].sum()) / nvalid if nvalid else np.float64('nan')
+    p = softmax64(z)
+    onehot = np.zeros_like(p)
+    np.put_along_axis(onehot, tgt[:, None], 1.0, axis=1)
+    gz = (p - onehot) * valid[:, None] * (grad_scale / nvalid if nvalid else 0.0)
+    return dict(loss=loss, nvalid=nvalid, argpred=z.argmax(axis=1), z=z,
+                grad_logits=bilinear.upsample_adjoint(gz, lo32.shape[2:]))

@@ -128,3 +128,16 @@ def chain_multi(lo1: torch.Tensor, lo2: torch.Tensor, out_hw, num_class: int, ki
     (loss_target + loss_target_2).backward()
     return dict(loss_target=loss_target.detach(), loss_target_2=loss_target_2.detach(), label_2=label_2,
                 nvalid=int((label_2 >= 0).sum()), grad1=x1.grad, grad2=x2.grad, hist=hist)
+
+
+def chain_source(logits_lo: torch.Tensor, target: torch.Tensor, num_class: int, grad_scale: float = 1.0):
+    """Source-side step (``tools/train_source.py:254,280-283``): upsample -> CrossEntropyLoss(ignore_index=-1)
+    -> backward, and the argmax map that goes into ``Eval.add_batch``.
+    Returns dict(loss, grad, argpred (numpy int64), nvalid)."""
+    import numpy as np
+    x = logits_lo.detach().clone().requires_grad_(True)
+    pred = F.interpolate(x, size=tuple(target.shape[-2:]), mode='bilinear', align_corners=True)
+    loss = F.cross_entropy(pred, target, ignore_index=-1)
+    (grad_scale * loss).backward()
+    argpred = np.argmax(pred.data.cpu().numpy(), axis=1)
+    return dict(loss=loss.detach(), grad=x.grad, argpred=argpred, nvalid=int((target != -1).sum()))
