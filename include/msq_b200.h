@@ -154,6 +154,21 @@ int msq_fused_bwd(int mode, const float* logits, int n, int num_class, int h, in
                   const void* aux /* nullable */, const float* grad_out, float* grad_logits,
                   int grad_is_zeroed, msq_stream_t stream);
 
+/* MinEnt baselines of the same loss factory (tools/solve_gta5.py:150-155): softCrossEntropy
+ * (mode MSQ_MODE_MAXSQUARE = unweighted) and IWsoftCrossEntropy (mode MSQ_MODE_IW) of
+ * utils/loss.py:17-67, called as the trainers call them -- target = softmax(inputs), attached to the
+ * graph (tools/solve_gta5.py:188-190,199) -- fused from the low-resolution head logits:
+ *   loss = mean(-p log p)                                   dL/dz_j = -(1/M) p_j (log p_j + H)
+ *   loss = sum_px w[argmax_c inputs] H_px / (N C)            H = -sum_c p_c log p_c
+ * (IWsoftCrossEntropy takes the argmax of the LOGITS and a C-bin histc, utils/loss.py:54-60).
+ * Buffers and outputs as msq_fused_fwd / msq_fused_bwd; aux is REQUIRED (the backward replays it). */
+int msq_entropy_fwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                    double ratio, int n_images_norm, void* accum, void* out, void* aux, float* zero_grad /* nullable */,
+                    msq_stream_t stream);
+int msq_entropy_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                    int n_images_norm, const void* out, const void* aux, const float* grad_out, float* grad_logits,
+                    int grad_is_zeroed, msq_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Multi-level self-produced guidance ("MaxSquare+IW+Multi", BASELINE config 3): the inline
  * trainer code tools/solve_gta5.py:183,192,206-215 == tools/solve_crosscity.py:235-243,

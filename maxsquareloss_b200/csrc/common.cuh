@@ -168,7 +168,7 @@ __device__ __forceinline__ float iw_weight(float hist, float total, float r32, f
 // one warp per image, one lane per class (C <= 32)
 // (any block size that is a multiple of 32, up to 256 threads; called by every thread of ONE CTA)
 __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                                              unsigned long long kept_dense, int multi) {
+                                              unsigned long long kept_dense, int multi, int loss_kind) {
     __shared__ double s_red[8];
     __shared__ unsigned long long s_cls[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
@@ -228,8 +228,13 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
         const unsigned long long kept_local = (kept_dense != 0ull) ? kept_dense : kept_ld;
         const double scale = (double)n_norm / (double)n;
         double loss;
-        if (mode == MSQ_MODE_IW) loss = -tot / ((double)n_norm * (double)C);
-        else loss = -tot / (2.0 * (double)kept_local * scale);
+        if (loss_kind == 0) {          // maximum squares: -sum(w p^2)/(N C)   |   -mean(p^2)/2
+            if (mode == MSQ_MODE_IW) loss = -tot / ((double)n_norm * (double)C);
+            else loss = -tot / (2.0 * (double)kept_local * scale);
+        } else {                       // entropy (utils/loss.py:32,65): sum(w H)/(N C)   |   mean(-p log p)
+            if (mode == MSQ_MODE_IW) loss = tot / ((double)n_norm * (double)C);
+            else loss = tot / ((double)kept_local * scale);
+        }
         if (flags_ld & kFlagNonFinite) loss = __longlong_as_double(0x7ff8000000000000LL);
         *st.loss = (float)loss;
         *st.kept_out = kept_local;
@@ -255,15 +260,15 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
 //   MaxSquare (utils/loss.py:118):     loss = -(sum q) / (2 * kept)
 // Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                    unsigned long long kept_dense, cudaStream_t stream, int multi = 0);
+                    unsigned long long kept_dense, cudaStream_t stream, int multi = 0, int loss_kind = 0);
 
 // fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
-                       float* zero_grad, cudaStream_t s);
+                       float* zero_grad, cudaStream_t s, int loss_kind = 0);
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
-                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s);
+                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind = 0);
 
 }  // namespace msq
 

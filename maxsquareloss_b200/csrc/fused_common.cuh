@@ -124,6 +124,54 @@ __device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], floa
     return k;
 }
 
+// MinEnt variant (utils/loss.py:17-67, softCrossEntropy / IWsoftCrossEntropy called with
+// target = softmax(inputs)): per pixel the entropy H = -sum_c p_c log p_c = ln s - A/s with
+// t_c = z_c - m, e_c = exp(t_c), s = sum e_c, A = sum e_c t_c (both terms are >= 0: no cancellation).
+// Returns H in `q`, D = A/s in `qs` and 1/s in `inv_s`;  dH/dz_j = -p_j (t_j - D).
+// The argmax is the reference's torch.max(inputs, 1) on the LOGITS (utils/loss.py:54): first maximum.
+template <int CT, bool NEED_ARG>
+__device__ __forceinline__ int pixel_stats_entropy(const float2 (&z)[(CT + 1) / 2], float& m_out, float& inv_s, float& q,
+                                                   float& qs) {
+    constexpr int CP = (CT + 1) / 2;
+    float m = z[0].x;
+#pragma unroll
+    for (int c = 1; c < CT; ++c) m = fmaxf(m, lane_of(z[c >> 1], c));
+    m_out = m;
+    int k = 0;
+    if (NEED_ARG) {
+        unsigned mask_a = 0u, mask_b = 0u;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            if (c & 1)
+                asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(mask_b) : "f"(z[c >> 1].y), "f"(m), "r"(1u << c));
+            else
+                asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(mask_a) : "f"(z[c >> 1].x), "f"(m), "r"(1u << c));
+        }
+        k = __ffs(mask_a | mask_b) - 1;
+        if (k < 0) k = 0;
+    }
+    const float2 l2e = splat(kLog2e), nm2 = splat(-m);
+    float2 sa = make_float2(0.f, 0.f), sb = sa, aa = sa, ab = sa;
+#pragma unroll
+    for (int p = 0; p < CP; ++p) {
+        const float2 t = __fadd2_rn(z[p], nm2);
+        const float2 tl = __fmul2_rn(t, l2e);
+        const float2 e = make_float2(ex2_approx(tl.x), ex2_approx(tl.y));
+        // padded lanes: t = -1e30, e = 0 exactly; keep 0 * -1e30 out of the sum
+        const float2 tc = make_float2(fmaxf(t.x, -1.0e4f), fmaxf(t.y, -1.0e4f));
+        if (p & 1) { sb = __fadd2_rn(sb, e); ab = __ffma2_rn(e, tc, ab); }
+        else { sa = __fadd2_rn(sa, e); aa = __ffma2_rn(e, tc, aa); }
+    }
+    const float2 s2 = __fadd2_rn(sa, sb), a2 = __fadd2_rn(aa, ab);
+    const float s = s2.x + s2.y, A = a2.x + a2.y;
+    inv_s = rcp_approx(s);
+    qs = A * inv_s;                 // D  (<= 0)
+    q = logf(s) - qs;               // H  (>= 0)
+    return k;
+}
+
 // Optional per-pixel statistics cache written by the forward and read by the backward: one
 // float4 per pixel {max logit m, q*s, 1/s^2, argmax class (int bits)} = 16 B/pixel, one
 // coalesced 128-bit store / load per thread and row.  With it the backward skips the max /
@@ -256,7 +304,7 @@ constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
 //     costs one conflict-free LDS.64/STS.64 pair, no atomics.  The buckets are reduced
 //     by warp shuffles at the end of the segment and merged with one global atomic per
 //     class and warp.
-template <int CT, bool PAD, bool IW, bool HAS_LABEL>
+template <int CT, bool PAD, bool IW, bool HAS_LABEL, int LOSS = 0>
 __global__ void __launch_bounds__(kTW, MSQ_FWD_MINB)
 fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, const int64_t* __restrict__ label,
                  State st, void* __restrict__ aux, float* __restrict__ zero_buf, unsigned zero_count) {
@@ -357,9 +405,10 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                 for (int p = 0; p < CP; ++p) z[p] = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
             }
             float m, inv_s, q, qs;
-            const int k = pixel_stats<CT, IW>(z, e, m, inv_s, q, qs);
+            const int k = (LOSS == 0) ? pixel_stats<CT, IW>(z, e, m, inv_s, q, qs)
+                                      : pixel_stats_entropy<CT, IW>(z, m, inv_s, q, qs);
             if (active) {
-                if (aux) axp[(long long)(y - sp.ys) * g.W] = make_float4(m, qs, inv_s * inv_s, __int_as_float(k));
+                if (aux) axp[(long long)(y - sp.ys) * g.W] = make_float4(m, qs, LOSS == 0 ? inv_s * inv_s : inv_s, __int_as_float(k));
                 if (IW) {
                     if (HAS_LABEL) {
                         const long long lv = label[((long long)sp.n * g.H + y) * g.W + x];
@@ -416,7 +465,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
 // cross-entropy on this head (tools/solve_gta5.py:213, nn.CrossEntropyLoss(ignore_index=-1)):
 //   dL/dz_c = (go / n_valid) * (p_c - [c == label_2])   for pixels with label_2 != -1
 // with {m, 1/s, label_2} read from the float4 cache msq_multi_fwd wrote for head 2.
-template <int CT, bool PAD, bool IW, bool CACHED, bool GUIDE = false>
+template <int CT, bool PAD, bool IW, bool CACHED, bool GUIDE = false, int LOSS = 0>
 __global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
 fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
                  const float* __restrict__ weights, const float* __restrict__ grad_out, float grad_out_value,
@@ -470,7 +519,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         }
         if (IW && sp.n != coef_img) {
             if (tid < g.C)
-                s_coef[tid] = (float)(-2.0 * (double)weights[sp.n * g.C + tid] * (double)go /
+                s_coef[tid] = (float)((LOSS == 0 ? -2.0 : -1.0) * (double)weights[sp.n * g.C + tid] * (double)go /
                                       ((double)n_norm * (double)g.C));
             coef_img = sp.n;
         }
@@ -609,6 +658,22 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                     const float2 ep = make_float2(ex2_approx(t.x), ex2_approx(t.y));
                     const float2 noh = make_float2(labf == (float)(2 * p) ? -1.f : 0.f, labf == (float)(2 * p + 1) ? -1.f : 0.f);
                     const float2 v = __ffma2_rn(ep, is, noh);
+                    dHa[p] = __ffma2_rn(a0, v, dHa[p]);
+                    dHb[p] = __ffma2_rn(a1, v, dHb[p]);
+                }
+            } else if (CACHED && LOSS == 1) {
+                // entropy: cache = {m, D, 1/s, k};  g_c = a e_c (t_c - D),  a = coef / s,  t_c = z_c - m
+                const float a = (IW ? s_coef[c_k] : coef_ms) * c_is2;
+                const float2 a0 = splat(a * ly0), a1 = splat(a * ly1), nD = splat(-c_qs);
+                const float2 l2e = splat(kLog2e), nm2 = splat(-c_m);
+#pragma unroll
+                for (int p = 0; p < CP; ++p) {
+                    const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
+                    const float2 t = __fadd2_rn(zp, nm2);
+                    const float2 tl = __fmul2_rn(t, l2e);
+                    const float2 ep = make_float2(ex2_approx(tl.x), ex2_approx(tl.y));
+                    const float2 tc = make_float2(fmaxf(t.x, -1.0e4f), fmaxf(t.y, -1.0e4f));
+                    const float2 v = __fmul2_rn(ep, __fadd2_rn(tc, nD));
                     dHa[p] = __ffma2_rn(a0, v, dHa[p]);
                     dHb[p] = __ffma2_rn(a1, v, dHb[p]);
                 }

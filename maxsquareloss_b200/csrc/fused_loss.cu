@@ -30,7 +30,7 @@ int g_fused_rows = 0;
 
 template <int CT, bool PAD>
 static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, const int64_t* label,
-                            float r32, float omr32, int nn, State st, void* aux, float* zero_buf, cudaStream_t s) {
+                            float r32, float omr32, int nn, State st, void* aux, float* zero_buf, cudaStream_t s, int loss_kind) {
     const unsigned zero_count = zero_buf ? (unsigned)((size_t)n * C * h * w) : 0u;
     const bool iw = mode != MSQ_MODE_MAXSQUARE;
 #define MSQ_LAUNCH(K)                                                                          \
@@ -43,18 +43,22 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
                                           label, st, aux, zero_buf, zero_count);              \
         if (le != cudaSuccess) return (int)le;                                                 \
     } while (0)
-    if (!iw) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, false, false>));
+    if (loss_kind == 1) {            // MinEnt losses: no label= argument in the reference (utils/loss.py:45)
+        if (label) return MSQ_E_BADARG;
+        if (!iw) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, false, false, 1>));
+        else MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, false, 1>));
+    } else if (!iw) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, false, false>));
     else if (label) MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, true>));
     else MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, false>));
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
-    return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s);
+    return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s, 0, loss_kind);
 }
 
 template <int CT, bool PAD>
 static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, int nn, State st,
                             const float* grad_out, float grad_out_value, float* grad_lo, const void* aux,
-                            bool grad_is_zeroed, cudaStream_t s) {
+                            bool grad_is_zeroed, cudaStream_t s, int loss_kind) {
     if (!grad_is_zeroed) {
         cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
         if (e != cudaSuccess) return (int)e;
@@ -70,7 +74,11 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
                                           (const unsigned long long*)nullptr);                                       \
         if (le != cudaSuccess) return (int)le;                                                                        \
     } while (0)
-    if (mode == MSQ_MODE_MAXSQUARE) {
+    if (loss_kind == 1) {            // MinEnt: the backward always replays the forward's cache
+        if (!aux) return MSQ_E_BADARG;
+        if (mode == MSQ_MODE_MAXSQUARE) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false, true, false, 1>));
+        else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, true, true, false, 1>));
+    } else if (mode == MSQ_MODE_MAXSQUARE) {
         if (aux) MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false, true>));
         else MSQ_LAUNCH((fused_bwd_kernel<CT, PAD, false, false>));
     } else {
@@ -99,7 +107,7 @@ namespace msq {
 
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
-                       float* zero_grad, cudaStream_t s) {
+                       float* zero_grad, cudaStream_t s, int loss_kind) {
     if (!logits || !accum || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES || h < 1 || w < 1 || out_h < 1 ||
         out_w < 1)
         return MSQ_E_BADARG;
@@ -108,14 +116,14 @@ int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int 
     const State st = carve(accum, out, n, num_class);
     const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s)
+#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s, loss_kind)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
 
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
-                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s) {
+                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind) {
     if (!logits || !out || !grad_logits || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES ||
         h < 1 || w < 1 || out_h < 1 || out_w < 1)
         return MSQ_E_BADARG;
@@ -123,7 +131,7 @@ int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int 
     if ((((uintptr_t)logits) | ((uintptr_t)grad_logits) | ((uintptr_t)grad_out)) & 3u) return MSQ_E_ALIGN;
     const State st = carve(nullptr, const_cast<void*>(out), n, num_class);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s)
+#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s, loss_kind)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
@@ -151,4 +159,27 @@ extern "C" int msq_fused_bwd(int mode, const float* logits, int n, int num_class
     if (((uintptr_t)aux) & 15u) return MSQ_E_ALIGN;
     return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, 0.f,
                                    grad_logits, aux, grad_is_zeroed, (cudaStream_t)stream);
+}
+
+// MinEnt baselines of the same factory (tools/solve_gta5.py:150-155): softCrossEntropy (mode MAXSQUARE =
+// unweighted) and IWsoftCrossEntropy (mode IW) of utils/loss.py:17-67, called as the trainers call them,
+// with target = softmax(inputs) (tools/solve_gta5.py:188-190,199), fused from the low-resolution logits.
+//   loss = mean(-p log p)                              (softCrossEntropy)
+//   loss = sum_px w[argmax logits] * H_px / (N C)      (IWsoftCrossEntropy; H = -sum_c p_c log p_c)
+// Same buffers and outputs as msq_fused_fwd / msq_fused_bwd; `aux` is required (the backward replays it).
+extern "C" int msq_entropy_fwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                               double ratio, int n_images_norm, void* accum, void* out, void* aux, float* zero_grad,
+                               msq_stream_t stream) {
+    if ((((uintptr_t)aux) & 15u) || (((uintptr_t)zero_grad) & 3u)) return MSQ_E_ALIGN;
+    return msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum, out,
+                                   aux, zero_grad, (cudaStream_t)stream, 1);
+}
+
+extern "C" int msq_entropy_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                               int n_images_norm, const void* out, const void* aux, const float* grad_out,
+                               float* grad_logits, int grad_is_zeroed, msq_stream_t stream) {
+    if (!grad_out || !aux) return MSQ_E_BADARG;
+    if (((uintptr_t)aux) & 15u) return MSQ_E_ALIGN;
+    return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, 0.f,
+                                   grad_logits, aux, grad_is_zeroed, (cudaStream_t)stream, 1);
 }

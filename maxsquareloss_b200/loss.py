@@ -270,6 +270,109 @@ class IW_MaxSquareloss(_LossBase):
         return self._run(pred, prob, label, out_size, self.ratio)
 
 
+class _EntropyLoss(torch.autograd.Function):
+    """MinEnt losses, fused from head logits (``msq_entropy_fwd`` / ``msq_entropy_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, logits, out_size, mode, ratio, n_norm, sink):
+        n, c, h, w = logits.shape
+        H, W = int(out_size[0]), int(out_size[1])
+        lo = logits.contiguous()
+        lib = _lib.load()
+        lay = _lib.state_layout(n, c)
+        accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
+        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
+        need = ctx.needs_input_grad[0]
+        aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device=lo.device)
+        grad = torch.empty_like(lo) if need else None
+        _lib.check(lib.msq_entropy_fwd(mode, lo.data_ptr(), n, c, h, w, H, W, float(ratio), int(n_norm), accum.data_ptr(),
+                                       out.data_ptr(), aux.data_ptr(), grad.data_ptr() if need else None, stream))
+        o = _Outputs(out, n, c)
+        sink.append(o)
+        ctx.save_for_backward(lo)
+        ctx.out, ctx.aux, ctx.grad = out, aux, grad
+        ctx.cfg = (mode, H, W, n_norm)
+        return o.loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        (lo,) = ctx.saved_tensors
+        mode, H, W, n_norm = ctx.cfg
+        n, c, h, w = lo.shape
+        go = _grad_out_ptr(grad_out, lo.device)
+        grad, zeroed = ctx.grad, 1
+        ctx.grad = None
+        if grad is None:
+            grad, zeroed = torch.empty_like(lo), 0
+        stream = torch.cuda.current_stream(lo.device).cuda_stream
+        _lib.check(_lib.load().msq_entropy_bwd(mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(),
+                                               ctx.aux.data_ptr(), go.data_ptr(), grad.data_ptr(), zeroed, stream))
+        return (grad,) + (None,) * 5
+
+
+class _EntropyBase(_LossBase):
+    def _run_entropy(self, inputs, target, out_size, ratio):
+        _require_cuda_f32(inputs, "inputs")
+        c = inputs.shape[1]
+        if c > _lib.MAX_CLASSES:
+            raise RuntimeError(f"{c} classes exceed the kernels' limit of {_lib.MAX_CLASSES}")
+        if self.num_class is not None:
+            self._check_classes(c)
+        if target is not None:
+            # strict call, as the trainers make it (tools/solve_gta5.py:188-190,199): target IS softmax(inputs),
+            # attached to the graph.  It is not read: the kernels recompute it, and the gradient returned for
+            # `inputs` is the total derivative through both arguments.
+            assert inputs.size() == target.size()                      # utils/loss.py:29,52
+            if out_size is not None and tuple(out_size) != tuple(inputs.shape[2:]):
+                raise RuntimeError("with a target tensor, inputs must already be at the target's resolution")
+            out_size = tuple(inputs.shape[2:])
+        elif out_size is None:
+            raise RuntimeError("fused mode needs out_size=(H, W): forward(head_logits, out_size=...)")
+        sink = []
+        loss = _EntropyLoss.apply(inputs, tuple(out_size), self._mode, ratio, self.global_batch, sink)
+        self._publish(sink)
+        return loss
+
+
+class softCrossEntropy(_EntropyBase):
+    """``mean(-log_softmax(inputs) * target)`` with ``target = softmax(inputs)`` (MinEnt,
+    ``utils/loss.py:17-35``; selected by ``--target_mode entropy``, ``tools/solve_gta5.py:150-151``)."""
+    _mode = _lib.MODE_MAXSQUARE
+
+    def __init__(self, ignore_index=-1):
+        super().__init__(ignore_index, None)
+
+    def forward(self, inputs, target=None, out_size=None):
+        """
+        :param inputs: predictions (N, C, H, W); in fused mode the low-resolution head logits (N, C, h, w)
+        :param target: target distribution (N, C, H, W) -- must be softmax(inputs), as every trainer passes it
+        :param out_size: (H, W) label resolution, fused mode only
+        :return: loss
+        """
+        return self._run_entropy(inputs, target, out_size, 0.0)
+
+
+class IWsoftCrossEntropy(_EntropyBase):
+    """Image-wise weighted MinEnt (``utils/loss.py:37-67``; ``--target_mode IW_entropy``): class weights
+    from the per-image histogram of ``argmax(inputs)``, as in ``IW_MaxSquareloss``."""
+    _mode = _lib.MODE_IW
+
+    def __init__(self, ignore_index=-1, num_class=19, ratio=0.2):
+        super().__init__(ignore_index, num_class)
+        self.ratio = ratio
+
+    def forward(self, inputs, target=None, out_size=None):
+        """
+        :param inputs: predictions (N, C, H, W); in fused mode the low-resolution head logits (N, C, h, w)
+        :param target: target distribution (N, C, H, W) -- must be softmax(inputs)
+        :param out_size: (H, W) label resolution, fused mode only
+        :return: loss with image-wise weighting factor
+        """
+        return self._run_entropy(inputs, target, out_size, self.ratio)
+
+
 def maxsquare_from_logits(head_logits, out_size, global_batch=0):
     """Functional fused MaxSquare loss from low-resolution head logits."""
     crit = MaxSquareloss(-1, head_logits.shape[1])

@@ -159,3 +159,30 @@ def source_ce(lo32: np.ndarray, target: np.ndarray, grad_scale: float = 1.0):
     gz = (p - onehot) * valid[:, None] * (grad_scale / nvalid if nvalid else 0.0)
     return dict(loss=loss, nvalid=nvalid, argpred=z.argmax(axis=1), z=z,
                 grad_logits=bilinear.upsample_adjoint(gz, lo32.shape[2:]))
+
+
+def fused_entropy(lo32: np.ndarray, out_hw, num_class: int, iw: bool, ratio: float = 0.2, grad_scale: float = 1.0):
+    """Closed form (float64) of softCrossEntropy / IWsoftCrossEntropy with target = softmax(inputs)
+    attached (``utils/loss.py:17-67`` as called at ``tools/solve_gta5.py:188-190,199``):
+        H_px   = -sum_c p_c log p_c
+        L      = sum_px H_px / (N C H W)                 (softCrossEntropy)
+        L      = sum_px w[n, argmax_c z] H_px / (N C)    (IW; argmax of the LOGITS, first maximum)
+        dL/dz_j = -coef_px * p_j (log p_j + H_px)        (total derivative through inputs and target)"""
+    z = bilinear.upsample(lo32, out_hw)
+    z64 = z.astype(np.float64)
+    p = softmax64(z)
+    logp = z64 - z64.max(axis=1, keepdims=True)
+    logp = logp - np.log(np.exp(logp).sum(axis=1, keepdims=True))
+    Hpx = -(p * logp).sum(axis=1, keepdims=True)
+    N = p.shape[0]
+    hist = None
+    if iw:
+        k = z.argmax(axis=1)
+        hist = class_hist_np(k, num_class)
+        w = weights_fp32(hist, ratio).astype(np.float64)
+        coef = np.take_along_axis(w[:, :, None, None], k[:, None, :, :], axis=1) / (N * num_class)
+    else:
+        coef = np.full_like(Hpx, 1.0 / p.size)
+    loss = (coef * Hpx).sum()
+    gz = -coef * p * (logp + Hpx) * grad_scale
+    return dict(loss=loss, hist=hist, grad_logits=bilinear.upsample_adjoint(gz, lo32.shape[2:]), z=z)

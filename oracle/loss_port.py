@@ -141,3 +141,46 @@ def chain_source(logits_lo: torch.Tensor, target: torch.Tensor, num_class: int, 
     (grad_scale * loss).backward()
     argpred = np.argmax(pred.data.cpu().numpy(), axis=1)
     return dict(loss=loss.detach(), grad=x.grad, argpred=argpred, nvalid=int((target != -1).sum()))
+
+
+def soft_cross_entropy(inputs: torch.Tensor, target: torch.Tensor, ignore_index: int = -1) -> torch.Tensor:
+    # utils/loss.py:29-35 (softCrossEntropy.forward)
+    assert inputs.size() == target.size()
+    keep = target != ignore_index
+    log_likelihood = F.log_softmax(inputs, dim=1)
+    return torch.mean(torch.mul(-log_likelihood, target)[keep])
+
+
+def iw_soft_cross_entropy(inputs: torch.Tensor, target: torch.Tensor, num_class: int, ratio: float = 0.2,
+                          ignore_index: int = -1, return_aux: bool = False):
+    # utils/loss.py:52-67 (IWsoftCrossEntropy.forward); the unsqueeze(1) is the N > 1 definition
+    # (see the module docstring: the reference broadcasts (N,H,W) against (N,C,H,W) and only works for N == 1)
+    assert inputs.size() == target.size()
+    keep = target != ignore_index
+    _, argpred = torch.max(inputs, 1)
+    n = inputs.size(0)
+    per_px, hists = [], []
+    for i in range(n):
+        hist = torch.histc(argpred[i].cpu().data.float(), bins=num_class, min=0, max=num_class - 1).float()
+        w = image_weights_from_hist(hist, ratio).to(argpred.device)[argpred[i]].detach()
+        per_px.append(w)
+        hists.append(hist)
+    weights = torch.stack(per_px, dim=0).unsqueeze(1)
+    log_likelihood = F.log_softmax(inputs, dim=1)
+    loss = torch.sum((torch.mul(-log_likelihood, target) * weights)[keep]) / (n * num_class)
+    if return_aux:
+        return loss, torch.stack(hists).to(torch.int64)
+    return loss
+
+
+def chain_entropy(logits_lo: torch.Tensor, out_hw, num_class: int, iw: bool, ratio: float = 0.2, grad_scale: float = 1.0):
+    """prologue -> MinEnt loss called as the trainers call it (target = softmax(pred), attached) -> backward."""
+    x = logits_lo.detach().clone().requires_grad_(True)
+    pred, prob = prologue(x, out_hw)
+    hist = None
+    if iw:
+        loss, hist = iw_soft_cross_entropy(pred, prob, num_class, ratio, return_aux=True)
+    else:
+        loss = soft_cross_entropy(pred, prob)
+    (grad_scale * loss).backward()
+    return loss.detach(), x.grad, hist
