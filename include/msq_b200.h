@@ -225,6 +225,12 @@ int msq_confusion_i64(const int64_t* gt, const int64_t* pred, int64_t npix, int 
 int msq_confusion_logits_f32(const int64_t* gt, const float* logits, int n, int num_class,
                              int64_t hw, unsigned long long* cm, msq_stream_t stream);
 
+/* Flip-ensemble evaluation (tools/evaluate.py:120-141, --flip), fused: argmax_c of
+ * (softmax(logits)[..., x] + softmax(logits_flipped)[..., W-1-x]) / 2 against gt, ACCUMULATED into cm.
+ * logits_flipped is the model's output for the horizontally flipped image, NOT flipped back. */
+int msq_confusion_flip_f32(const int64_t* gt, const float* logits, const float* logits_flipped, int n, int num_class,
+                           int out_h, int out_w, unsigned long long* cm, msq_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Host-buffer pipeline (the one part of the library that owns memory): the fused
  * step for callers whose tensors live in HOST memory.  Each submission copies the

@@ -16,7 +16,7 @@ MODE_IW = 1
 
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
-           "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_tune_set",
+           "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
            "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
@@ -73,6 +73,8 @@ def load():
         lib.msq_source_ce_fwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.msq_fused_aux_bytes.restype = i64
         lib.msq_fused_aux_bytes.argtypes = [i32, i32, i32]
+        lib.msq_confusion_flip_f32.restype = i32
+        lib.msq_confusion_flip_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
         lib.msq_confusion_i64.restype = i32
         lib.msq_confusion_i64.argtypes = [vp, vp, i64, i32, vp, vp, vp]
         lib.msq_confusion_logits_f32.restype = i32

@@ -105,6 +105,25 @@ class Eval:
                                                         self._dev.data_ptr(), stream))
         self._pending = True
 
+    def add_batch_flip(self, gt_image, logits, logits_flipped):
+        """Flip-ensemble evaluation (``tools/evaluate.py:120-141`` with ``--flip``), fused on the device:
+        ``argmax((softmax(logits) + flip(softmax(logits_flipped), -1)) / 2)`` against ``gt_image``.
+        ``logits_flipped`` is the model's output for the horizontally flipped input, not flipped back."""
+        for t, name in ((logits, "logits"), (logits_flipped, "logits_flipped")):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
+                raise RuntimeError(f"{name} must be a float32 CUDA tensor (N,C,H,W)")
+        assert tuple(logits.shape) == tuple(logits_flipped.shape)
+        n, c, h, w = logits.shape
+        assert tuple(gt_image.shape) == (n, h, w)
+        if c != self.num_class:
+            raise ValueError(f"logits have {c} classes, Eval was built with {self.num_class}")
+        gt = _to_device_labels(gt_image, self.device, self.num_class, True)
+        la, lb = logits.contiguous(), logits_flipped.contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().msq_confusion_flip_f32(gt.data_ptr(), la.data_ptr(), lb.data_ptr(), n, c, h, w,
+                                                      self._dev.data_ptr(), stream))
+        self._pending = True
+
     def _fold(self):
         """device counts -> host float64 matrix (one small D2H, synchronises)."""
         if not self._pending:

@@ -87,3 +87,23 @@ class EvalPort:
         if out_16_13:
             return tot(fw[SYNTHIA_16_OF_19]), tot(fw[SYNTHIA_13_OF_19])
         return tot(fw)
+
+
+def flip_ensemble_argmax(pred, pred_flip):
+    """``tools/evaluate.py:120-136`` (``--flip``): softmax of the prediction and of the prediction for the
+    horizontally flipped image, the latter flipped back, averaged; ``np.argmax`` over classes.
+    ``pred`` / ``pred_flip``: torch tensors (N,C,H,W) as the model returns them.  -> numpy int64 (N,H,W)."""
+    import torch
+    import torch.nn.functional as F
+
+    def flip(x, dim):                                   # evaluate.py:122-127
+        dim = x.dim() + dim if dim < 0 else dim
+        inds = tuple(slice(None, None) if i != dim
+                     else x.new(torch.arange(x.size(i) - 1, -1, -1).tolist()).long()
+                     for i in range(x.dim()))
+        return x[inds]
+    pred_P = F.softmax(pred, dim=1)
+    pred_P_flip = F.softmax(pred_flip, dim=1)
+    pred_P_2 = flip(pred_P_flip, -1)
+    pred_c = (pred_P + pred_P_2) / 2
+    return np.argmax(pred_c.data.cpu().numpy(), axis=1)

@@ -146,3 +146,43 @@ def test_full_size_properties(msq):
     assert np.array_equal(ev2.confusion_matrix, cm)
     miou = ev.Mean_Intersection_over_Union()
     assert isinstance(miou, tuple) and len(miou) == 2          # 16-class Eval returns (mIoU16, mIoU13)
+
+
+# ------------------------------------------------------------------ flip-ensemble evaluation (tools/evaluate.py:120-141)
+@pytest.mark.parametrize("C,shape,scale", [(19, (2, 64, 128), 3.0), (16, (1, 40, 72), 1.0), (13, (1, 33, 65), 5.0),
+                                           (7, (2, 9, 31), 2.0), (19, (1, 512, 1024), 4.0), (19, (1, 17, 3), 0.01)])
+def test_flip_ensemble_vs_oracle(msq, C, shape, scale):
+    from oracle import eval_port
+    n, h, w = shape
+    g = torch.Generator().manual_seed(C * 1000 + w)
+    a = torch.randn(n, C, h, w, generator=g) * scale
+    b = torch.flip(a, dims=[-1]) + 0.5 * scale * torch.randn(n, C, h, w, generator=g)     # a flipped view of a similar scene
+    gt = synth.blocky_labels(n, (h, w), C, 17, grid=(4, 8))
+    arg = eval_port.flip_ensemble_argmax(a, b)                    # CPU torch arithmetic
+    arg_dev = eval_port.flip_ensemble_argmax(a.cuda(), b.cuda())  # the same ops on this GPU (what the reference runs)
+    port = eval_port.EvalPort(C)
+    port.add_batch(gt.numpy(), arg_dev)
+    ev = msq.Eval(C)
+    ev.add_batch_flip(gt.cuda(), a.cuda(), b.cuda())
+    assert np.array_equal(ev.confusion_matrix, port.confusion_matrix)
+    # CPU and CUDA softmax may round differently: any disagreement must be a pixel whose two best averaged
+    # probabilities are within a few ulps
+    assert (arg != arg_dev).mean() < 1e-4
+    ev2 = msq.Eval(C)
+    ev2.add_batch(gt.cuda(), torch.from_numpy(arg_dev).cuda())
+    assert np.array_equal(ev.confusion_matrix, ev2.confusion_matrix)
+    assert ev.Mean_Intersection_over_Union() == ev2.Mean_Intersection_over_Union() or C == 16
+
+
+def test_flip_ensemble_identical_views_reduce_to_plain_argmax(msq):
+    a = torch.randn(1, 19, 32, 48) * 3
+    gt = synth.random_labels(1, (32, 48), 19, 2)
+    ev = msq.Eval(19)
+    ev.add_batch_flip(gt.cuda(), a.cuda(), torch.flip(a, dims=[-1]).cuda())
+    ref = msq.Eval(19)
+    ref.add_batch_logits(gt.cuda(), a.cuda())
+    assert np.array_equal(ev.confusion_matrix, ref.confusion_matrix)
+    with pytest.raises(AssertionError):
+        ev.add_batch_flip(gt.cuda(), a.cuda(), a[:, :, :16].cuda())
+    with pytest.raises(RuntimeError):
+        ev.add_batch_flip(gt, a, a)
