@@ -380,6 +380,8 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and not args.skip_secondary:
         kernels += secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit)
         extra["maxsquare"] = maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, aux_ptrs, acc_ptr, go_ptr, n_norm, stream, kit)
+        extra["next_rows"] = next_rows(lib, _lib, synth, dev, stream, kit)
+        extra["torch_cuda_eager_baseline"] = torch_eager_gpu(dev)
     dom = max(kernels[:2], key=lambda k: k["ms"])
     traffic, traffic_src = None, None
     try:        # DRAM bytes of one launch from the committed ncu --set full capture of this workload
@@ -474,7 +476,103 @@ def secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit):
     byt = (4.0 * C + 8) * px_src
     out.append({"kernel": "confusion_logits_kernel<19> (argmax fused)", "bound": "hbm", "algorithmic_bytes": byt, "ms": t,
                 "achieved_GBps": byt / t / 1e6, "frac_of_hbm": byt / t / 1e6 / hbm_peak, "gpixel_per_s": px_src / t / 1e6})
+    del lgs
+    # flip-ensemble evaluation (tools/evaluate.py --flip): two logits tensors + labels, one pass
+    fa = [torch.randn(N_IMG, C, *HW_OUT, device=dev) * 3 for _ in range(2)]
+    fb = [torch.flip(a, dims=[-1]) + torch.randn_like(a) for a in fa]
+    gtf = [synth.blocky_labels(N_IMG, HW_OUT, C, 300 + i).to(dev) for i in range(2)]
+    f = lambda i: lib.msq_confusion_flip_f32(gtf[i % 2].data_ptr(), fa[i % 2].data_ptr(), fb[i % 2].data_ptr(), N_IMG, C,
+                                             HW_OUT[0], HW_OUT[1], cm.data_ptr(), stream)
+    t = time_loop(f, kit, 5)
+    byt = (8.0 * C + 8) * npx
+    out.append({"kernel": "confusion_flip_kernel<19> (2 softmaxes + mirrored average + argmax fused)", "bound": "hbm",
+                "algorithmic_bytes": byt, "ms": t, "achieved_GBps": byt / t / 1e6, "frac_of_hbm": byt / t / 1e6 / hbm_peak,
+                "gpixel_per_s": npx / t / 1e6})
+    del fa, fb
     return out
+
+
+def next_rows(lib, _lib, synth, dev, stream, kit):
+    """Steps of the rows built after the headline path: multi-level guidance (cfg 3), the MinEnt
+    losses, and the source-side CE + Eval step, each fused from low-resolution logits; us per step and Gpix/s."""
+    res = {}
+    kit = min(kit, 200)
+    h, w = HW_LO
+    H, W = HW_OUT
+    pool = 16
+    lay = _lib.state_layout(N_IMG, C)
+    accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=dev)
+    go = torch.full((), LAMBDA_TARGET, device=dev)
+    lo1 = torch.randn(pool, N_IMG, C, h, w, device=dev) * 5
+    lo2 = lo1 + 0.5 * torch.randn_like(lo1)
+    g1, g2 = torch.empty_like(lo1), torch.empty_like(lo2)
+    nb = lib.msq_fused_aux_bytes(N_IMG, H, W)
+    aux1 = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(4)]
+    aux2 = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(4)]
+
+    def multi(i):
+        j, a = i % pool, i % 4
+        lib.msq_multi_fwd(_lib.MODE_IW, lo1[j].data_ptr(), lo2[j].data_ptr(), N_IMG, C, h, w, H, W, RATIO, 0.95, 0,
+                          accum.data_ptr(), out.data_ptr(), aux1[a].data_ptr(), aux2[a].data_ptr(), g1[j].data_ptr(),
+                          g2[j].data_ptr(), None, stream)
+        lib.msq_fused_bwd(_lib.MODE_IW, lo1[j].data_ptr(), N_IMG, C, h, w, H, W, 0, out.data_ptr(), aux1[a].data_ptr(),
+                          go.data_ptr(), g1[j].data_ptr(), 1, stream)
+        lib.msq_guidance_bwd(lo2[j].data_ptr(), N_IMG, C, h, w, H, W, out.data_ptr(), aux2[a].data_ptr(), go.data_ptr(),
+                             g2[j].data_ptr(), 1, stream)
+    t = time_loop(multi, kit, 20)
+    res["multi_level_guidance"] = {"what": "cfg3 step per GPU: IW-MaxSquare on head 1 + self-produced guidance CE on head 2, "
+                                           "fwd + both backwards (batch 2, 65x129 -> 512x1024)",
+                                   "us_per_step": t * 1e3, "gpixel_per_s": PX_PER_STEP / t / 1e6, "launches_per_step": 4}
+
+    def ent(i):
+        j, a = i % pool, i % 4
+        lib.msq_entropy_fwd(_lib.MODE_IW, lo1[j].data_ptr(), N_IMG, C, h, w, H, W, RATIO, 0, accum.data_ptr(), out.data_ptr(),
+                            aux1[a].data_ptr(), g1[j].data_ptr(), stream)
+        lib.msq_entropy_bwd(_lib.MODE_IW, lo1[j].data_ptr(), N_IMG, C, h, w, H, W, 0, out.data_ptr(), aux1[a].data_ptr(),
+                            go.data_ptr(), g1[j].data_ptr(), 1, stream)
+    t = time_loop(ent, kit, 20)
+    res["iw_entropy"] = {"what": "IWsoftCrossEntropy fwd+bwd, same shape", "us_per_step": t * 1e3,
+                         "gpixel_per_s": PX_PER_STEP / t / 1e6, "launches_per_step": 3}
+
+    # source-side step of cfg 2: 2 x 19 x 91x161 -> 720x1280, CE + argmax + confusion matrix, then backward
+    hs, ws, Hs, Ws = 91, 161, 720, 1280
+    los = torch.randn(pool, N_IMG, C, hs, ws, device=dev) * 3
+    gs = torch.empty_like(los)
+    ys = [synth.blocky_labels(N_IMG, (Hs, Ws), C, 500 + i).to(dev) for i in range(4)]
+    auxs = [torch.empty(lib.msq_fused_aux_bytes(N_IMG, Hs, Ws), dtype=torch.uint8, device=dev) for _ in range(4)]
+    cm = torch.zeros(C * C + 1, dtype=torch.int64, device=dev)
+
+    def src(i):
+        j, a = i % pool, i % 4
+        lib.msq_source_ce_fwd(los[j].data_ptr(), ys[a].data_ptr(), N_IMG, C, hs, ws, Hs, Ws, accum.data_ptr(), out.data_ptr(),
+                              auxs[a].data_ptr(), gs[j].data_ptr(), cm.data_ptr(), stream)
+        lib.msq_guidance_bwd(los[j].data_ptr(), N_IMG, C, hs, ws, Hs, Ws, out.data_ptr(), auxs[a].data_ptr(), go.data_ptr(),
+                             gs[j].data_ptr(), 1, stream)
+    t = time_loop(src, kit, 20)
+    px = N_IMG * Hs * Ws
+    res["source_ce_eval"] = {"what": "cfg2 source step per GPU: CrossEntropyLoss + argmax + confusion matrix fwd, CE bwd "
+                                     "(batch 2, 91x161 -> 720x1280)", "us_per_step": t * 1e3, "gpixel_per_s": px / t / 1e6,
+                             "launches_per_step": 3}
+    return res
+
+
+def torch_eager_gpu(dev, iters=20):
+    """Secondary baseline: the reference's op chain executed by torch eager on this GPU (what a user of the
+    reference actually runs today): F.interpolate -> softmax -> IW loss (with its per-image D2H + CPU histc + H2D)
+    -> backward.  Oracle port, timed beside the CUDA path, never part of it."""
+    from oracle import loss_port
+    lo = torch.randn(N_IMG, C, *HW_LO, device=dev) * 5
+    for _ in range(3):
+        loss_port.chain_iw_maxsquare(lo, HW_OUT, C, RATIO, LAMBDA_TARGET)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        loss_port.chain_iw_maxsquare(lo, HW_OUT, C, RATIO, LAMBDA_TARGET)
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / iters
+    return {"value": PX_PER_STEP / t / 1e9, "unit": UNIT, "ms_per_step": t * 1e3,
+            "what": "reference op chain (oracle port) on torch CUDA eager, same GPU, device-resident input"}
 
 
 def maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, aux_ptrs, acc_ptr, go_ptr, n_norm, stream, kit):
