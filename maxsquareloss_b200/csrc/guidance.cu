@@ -43,8 +43,12 @@ __device__ __noinline__ int resolve_guidance(const float* z1, const float* z2, f
     return (max1 > thr || max2 > thr) ? arg : -1;
 }
 
+#ifndef MSQ_MULTI_MINB
+#define MSQ_MULTI_MINB 2
+#endif
+
 template <int CT, bool PAD, bool IW>
-__global__ void __launch_bounds__(kTW, 3)
+__global__ void __launch_bounds__(kTW, MSQ_MULTI_MINB)
 multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, FusedGeo g, int n_img, unsigned units,
                  float thr, State st, void* __restrict__ aux1, void* __restrict__ aux2, float* __restrict__ zero1,
                  float* __restrict__ zero2, unsigned zero_count, long long* __restrict__ label_out) {
@@ -178,15 +182,14 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
             for (int c = 1; c < CT; ++c) bv = fmaxf(bv, lane_of(pc[c >> 1], c));
             const float near = bv - bv * kCloseRel;
             unsigned mask_a = 0u, mask_b = 0u;
-            float zsel = 0.f;            // head-2 logit of the selected class
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
                 if (c & 1)
-                    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %2, %3;\n\t@p or.b32 %0, %0, %4;\n\t@p mov.f32 %1, %5;\n\t}"
-                        : "+r"(mask_b), "+f"(zsel) : "f"(pc[c >> 1].y), "f"(near), "r"(1u << c), "f"(z2[c >> 1].y));
+                    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                        : "+r"(mask_b) : "f"(pc[c >> 1].y), "f"(near), "r"(1u << c));
                 else
-                    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %2, %3;\n\t@p or.b32 %0, %0, %4;\n\t@p mov.f32 %1, %5;\n\t}"
-                        : "+r"(mask_a), "+f"(zsel) : "f"(pc[c >> 1].x), "f"(near), "r"(1u << c), "f"(z2[c >> 1].x));
+                    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                        : "+r"(mask_a) : "f"(pc[c >> 1].x), "f"(near), "r"(1u << c));
             }
             const unsigned mask = mask_a | mask_b;
             int lab = __ffs(mask) - 1;
@@ -199,7 +202,6 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
 #pragma unroll
                 for (int c = 0; c < CT; ++c) { zl1[c] = lane_of(z1[c >> 1], c); zl2[c] = lane_of(z2[c >> 1], c); }
                 lab = resolve_guidance<CT>(zl1, zl2, m1, m2, thr);
-                zsel = zl2[lab < 0 ? 0 : lab];
             } else if (!valid_fast) {
                 lab = -1;
             }
@@ -209,6 +211,13 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
                 if (aux2) ax2[px] = make_float4(m2, is2, __int_as_float(lab), 0.f);
                 if (label_out) label_out[px] = (long long)lab;
                 if (lab >= 0) {                    // -log softmax(z2)[lab] = m2 + ln(s2) - z2[lab]
+                    // z2[lab] re-derived from the tile with the very same arithmetic (cheaper than a C-way select)
+                    constexpr int CPD = cpd(CT);
+                    const float* t0 = s_tile2 + ((y0 - sp.r_lo) * g.ncp) * CPD + lab;
+                    const float* t1 = s_tile2 + ((y1 - sp.r_lo) * g.ncp) * CPD + lab;
+                    const float ha = __fmaf_rn(t0[j0 * CPD], lx0, __fmul_rn(t0[j1 * CPD], lx1));
+                    const float hb = __fmaf_rn(t1[j0 * CPD], lx0, __fmul_rn(t1[j1 * CPD], lx1));
+                    const float zsel = __fmaf_rn(ha, ly0, __fmul_rn(hb, ly1));
                     ce_run += (m2 - zsel) + logf(s2);        // full-precision log: lg2.approx's 2^-22 absolute error is a bias at -log p ~ 1e-2
                     nvalid++;
                 }
@@ -274,7 +283,7 @@ static int launch_multi_fwd(int mode, const float* lo1, const float* lo2, int C,
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
         LaunchPlan lp;                                                                         \
-        const int rc = plan_launch(K, C, h, w, H, W, n, 3,                                     \
+        const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_MULTI_MINB,                                   \
                                    [&](const FusedGeo& g) { return multi_smem(g, iw, CT); }, lp); \
         if (rc) return rc;                                                                     \
         const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo1, lo2, lp.p.g, n, (unsigned)lp.p.units, \
