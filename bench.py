@@ -198,7 +198,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from maxsquareloss_b200 import build as _build
     if rank == 0:
         _build.build()          # no-op when lib/libmsq_b200.so is up to date; never a fallback: load() raises if absent
@@ -247,23 +248,23 @@ def run_b200(args, rank, world, local_rank):
             _lib.check(rc)
 
     pending = []
+    comm = mdist.StatsComm() if world > 1 else None
+    stats_ptrs = [v.data_ptr() for v in stats_views]
+    n_stats = 1 + C
 
     def step(i):
         fwd(i)
-        if world > 1:      # one small all-reduce per step, overlapped with the backward kernel
-            pending.append(dist.all_reduce(stats_views[i % POOL], async_op=True))
+        if world > 1:      # one small all-reduce per step (NCCL, side stream), overlapped with the backward kernel
+            comm.join(stream)          # order this stream after the PREVIOUS step's collective (it had a whole step)
+            comm.allreduce_ptr(stats_ptrs[i % POOL], n_stats, stream)
         bwd(i)
-        if world > 1 and len(pending) >= 2:
-            pending.pop(0).wait()
 
-    # ---- warm-up: at least W steps and at least ~0.3 s so the clocks are up
-    t0 = time.perf_counter()
-    i = 0
-    min_warm_s = float(os.environ.get("MSQ_BENCH_MIN_WARM_S", "0.3"))     # 0 under ncu
-    while i < warm or time.perf_counter() - t0 < min_warm_s:
+    # ---- warm-up: at least W steps, and enough of them (~0.2 s) for the clocks to be up.  The count is FIXED, not
+    #      time-based: every rank must issue the same number of all-reduces
+    warm_steps = warm if os.environ.get("MSQ_BENCH_MIN_WARM_S") == "0" else max(warm, 5000)      # "0": under ncu
+    for i in range(warm_steps):
         step(i)
-        i += 1
-        if i % 256 == 0:
+        if i % 256 == 255:
             torch.cuda.synchronize()
     for wk in pending:
         wk.wait()
@@ -280,9 +281,8 @@ def run_b200(args, rank, world, local_rank):
     ev0.record()
     for i in range(steps):
         step(i)
-    for wk in pending:
-        wk.wait()
-    pending.clear()
+    if comm is not None:
+        comm.join(stream)
     ev1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()

@@ -36,6 +36,7 @@ extern "C" {
 #define MSQ_E_BADARG   (-1)         /* null pointer, non-positive size, C > MSQ_MAX_CLASSES */
 #define MSQ_E_GEOMETRY (-2)         /* fused path needs H >= h and W >= w (the model only upsamples) */
 #define MSQ_E_SMEM     (-3)         /* tile does not fit shared memory */
+#define MSQ_E_NCCL     (-5)         /* libnccl.so.2 could not be loaded, or an NCCL call failed */
 #define MSQ_E_ALIGN    (-4)         /* pointer not aligned for its element type */
 
 #define MSQ_MODE_MAXSQUARE 0        /* utils/loss.py:104-119  MaxSquareloss      */
@@ -254,6 +255,23 @@ void msq_pipe_destroy(msq_pipe* pipe);
 /* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "conf_ctas" 1|2,
  * "prob_waves" W, "fused_rows" R; 0 = automatic).  Results never depend on them. */
 int msq_tune_set(const char* key, int value);
+
+/* ---------------------------------------------------------------------------
+ * The one exchange of the image-sharded path: all-reduce(sum) of the packed fp64
+ * statistics vector [loss | class hist(C) | confusion(C*C)] over NCCL / NVLink, enqueued by this
+ * library on a communicator of its own (no torch.distributed call per step: ProcessGroupNCCL costs
+ * ~25 us of host time per collective, most of a 35 us step).  Rank 0 calls msq_comm_unique_id and
+ * hands the 128 bytes to the other ranks (any transport; the Python side uses a torch.distributed
+ * broadcast); every rank then calls msq_comm_create (collective).  msq_comm_allreduce_f64 forks a
+ * side stream from `stream`, so the collective overlaps whatever the caller enqueues next (the
+ * backward kernel); msq_comm_join makes `stream` wait for it.  libnccl.so.2 is dlopen'ed.
+ * ------------------------------------------------------------------------- */
+typedef struct msq_comm msq_comm;
+int msq_comm_unique_id(void* id128 /* host, 128 bytes */);
+int msq_comm_create(const void* id128, int world, int rank, msq_comm** out);
+int msq_comm_allreduce_f64(msq_comm* comm, double* buf /* device, in place */, int count, msq_stream_t stream);
+int msq_comm_join(msq_comm* comm, msq_stream_t stream);
+void msq_comm_destroy(msq_comm* comm);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmsq_b200.so")
-SOURCES = ["api.cu", "confusion.cu", "eval_flip.cu", "prob_loss.cu", "fused_loss.cu", "guidance.cu", "source_ce.cu", "host_pipe.cu"]
+SOURCES = ["api.cu", "confusion.cu", "eval_flip.cu", "prob_loss.cu", "fused_loss.cu", "guidance.cu", "source_ce.cu", "host_pipe.cu", "comm.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "fused_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "msq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC",
@@ -72,7 +72,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             if err:
                 sys.stderr.write(err)
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared",
-            "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", out + ".tmp"] + [o for o, _ in results]
+            "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-ldl", "-o", out + ".tmp"] + [o for o, _ in results]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)

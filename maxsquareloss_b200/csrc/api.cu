@@ -41,6 +41,7 @@ extern "C" const char* msq_error_string(int code) {
         case MSQ_E_GEOMETRY: return "msq: fused path needs out_h >= h and out_w >= w (bilinear upsampling only)";
         case MSQ_E_SMEM: return "msq: low-resolution tile does not fit in shared memory";
         case MSQ_E_ALIGN: return "msq: pointer is not aligned for its element type";
+        case MSQ_E_NCCL: return "msq: libnccl.so.2 could not be loaded, or an NCCL call failed";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "msq: unknown error";
     }
 }

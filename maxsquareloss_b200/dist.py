@@ -61,3 +61,59 @@ def allreduce_stats(buf, group=None, async_op=False):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
     return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class StatsComm:
+    """The per-step all-reduce of the packed statistics vector, enqueued by libmsq_b200 on an NCCL communicator
+    of its own (C ABI ``msq_comm_*``): one ``ncclAllReduce`` on a side stream per call and ~3 us of host time,
+    against ~25 us for ``torch.distributed.all_reduce``.  ``torch.distributed`` is used once, to hand rank 0's
+    NCCL unique id to the other ranks.  CUDA only."""
+
+    def __init__(self, group=None):
+        import ctypes
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("StatsComm needs an initialised torch.distributed process group (for the unique id)")
+        self._libmod = _lib
+        self._lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(self._lib.msq_comm_unique_id(ident))
+        t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = t.to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.msq_comm_create(raw, self.world, self.rank, ctypes.byref(h)))
+        self._h = h
+
+    def allreduce(self, buf):
+        """Sum the float64 CUDA vector ``buf`` over the ranks, in place, asynchronously w.r.t. the current stream."""
+        if not (buf.is_cuda and buf.dtype == torch.float64 and buf.is_contiguous()):
+            raise RuntimeError("StatsComm.allreduce needs a contiguous float64 CUDA tensor")
+        stream = torch.cuda.current_stream(buf.device).cuda_stream
+        self._libmod.check(self._lib.msq_comm_allreduce_f64(self._h, buf.data_ptr(), buf.numel(), stream))
+
+    def allreduce_ptr(self, ptr, count, stream):
+        rc = self._lib.msq_comm_allreduce_f64(self._h, ptr, count, stream)
+        if rc:
+            self._libmod.check(rc)
+
+    def join(self, stream=None):
+        """Make the current stream wait for the most recent ``allreduce`` (no host synchronisation)."""
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        self._libmod.check(self._lib.msq_comm_join(self._h, stream))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.msq_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
