@@ -15,7 +15,7 @@ at 65x129).  Metric: Gpixel/s = label-resolution pixels / time.
          autograd) with pinned HOST logits in and the loss + dL/dlogits back on the host
 
 Weak scaling: every rank owns its own 2 images (sharding by image); for N > 1 each step
-also all-reduces the packed [loss, class histogram] vector over NCCL, overlapped with
+also all-reduces the packed [loss, class histogram] vector over NCCL (dist.StatsComm), overlapped with
 the backward kernel.
 
 ``--impl reference`` times the reference's algorithm on the host CPU (oracle/loss_port.py:
@@ -249,15 +249,20 @@ def run_b200(args, rank, world, local_rank):
 
     pending = []
     comm = mdist.StatsComm() if world > 1 else None
+    if world > 1:
+        _lib.tune("reserve_sms", int(os.environ.get("MSQ_RESERVE_SMS", "0")))      # room for the NCCL kernel next to the one-wave grids
     stats_ptrs = [v.data_ptr() for v in stats_views]
     n_stats = 1 + C
 
     def step(i):
         fwd(i)
-        if world > 1:      # one small all-reduce per step (NCCL, side stream), overlapped with the backward kernel
-            comm.join(stream)          # order this stream after the PREVIOUS step's collective (it had a whole step)
-            comm.allreduce_ptr(stats_ptrs[i % POOL], n_stats, stream)
         bwd(i)
+        if world > 1:
+            # one small all-reduce per step (NCCL, side stream).  It is forked AFTER the backward so that no stream
+            # operation sits between forward -> finalise -> backward (that would break their programmatic dependent
+            # launches); it overlaps the next step's kernels, and this stream is ordered after the PREVIOUS collective.
+            comm.join(stream)
+            comm.allreduce_ptr(stats_ptrs[i % POOL], n_stats, stream)
 
     # ---- warm-up: at least W steps, and enough of them (~0.2 s) for the clocks to be up.  The count is FIXED, not
     #      time-based: every rank must issue the same number of all-reduces
@@ -410,8 +415,8 @@ def run_b200(args, rank, world, local_rank):
                 "config": {"workload": WORKLOAD, "images_per_gpu": N_IMG, "global_batch": n_norm,
                            "l2_policy": f"inputs rotate over {POOL} distinct logits buffers "
                                         f"({POOL * lo_bytes / 1e6:.0f} MB > 126 MB L2); outputs likewise",
-                           "parallelism": f"image-sharded x{world}" + (", 1 NCCL all-reduce of [loss,hist] per step "
-                                                                        "overlapped with backward" if world > 1 else "")},
+                           "parallelism": f"image-sharded x{world}" + (", 1 NCCL all-reduce of [loss,hist] per step on the library's own "
+                                                                        "communicator, overlapped with the next step" if world > 1 else "")},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lo_bytes),
                         "d2h_bytes_per_step": int(lo_bytes) + 4, "steps": e2e_steps,

@@ -715,6 +715,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
 
 // ------------------------------------------------------------------ host side
 extern int g_fused_rows;   // tuning knob (fused_loss.cu): 0 = automatic (one balanced wave), R = about R rows per CTA
+extern int g_reserve_sms;  // SMs left free by the one-wave grids (for a concurrent NCCL kernel when sharded)
 
 static inline int sm_count() {
     static int n = 0;
@@ -776,7 +777,8 @@ static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_p
     const int tiles_x = (W + kTW - 1) / kTW;
     p.units = (long long)n * tiles_x * H;
     if (p.units >= (1LL << 31)) return MSQ_E_GEOMETRY;
-    long long grid = (long long)sm_count() * ctas_per_sm;
+    const int sms = sm_count() - (g_reserve_sms > 0 && g_reserve_sms < sm_count() ? g_reserve_sms : 0);
+    long long grid = (long long)sms * ctas_per_sm;
     if (g_fused_rows > 0) grid = (p.units + g_fused_rows - 1) / g_fused_rows;
     else if (p.units / grid < 4) grid = p.units / 4;          // tiny problems: at least 4 rows per CTA
     if (grid < 1) grid = 1;
@@ -836,7 +838,7 @@ static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
 // plan + shared-memory size for `kernel`, compiled for `minb` co-resident CTAs per SM
 template <typename K, typename SmemFn>
 static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp) {
-    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows};
+    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows + 100000 * g_reserve_sms};
     if (plan_cache(key, lp, false)) return 0;
     int rc = make_plan(C, h, w, H, W, n, minb, lp.p);
     if (rc) return rc;

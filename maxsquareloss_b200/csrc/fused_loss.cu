@@ -27,6 +27,7 @@
 namespace msq {
 
 int g_fused_rows = 0;
+int g_reserve_sms = 0;
 
 template <int CT, bool PAD>
 static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, const int64_t* label,
