@@ -248,6 +248,7 @@ def run_b200(args, rank, world, local_rank):
             _lib.check(rc)
 
     pending = []
+    COMM_LAG = int(os.environ.get("MSQ_COMM_LAG", "0"))
     comm = mdist.StatsComm() if world > 1 else None
     if world > 1:
         _lib.tune("reserve_sms", int(os.environ.get("MSQ_RESERVE_SMS", "0")))      # room for the NCCL kernel next to the one-wave grids
@@ -261,7 +262,7 @@ def run_b200(args, rank, world, local_rank):
             # one small all-reduce per step (NCCL, side stream).  It is forked AFTER the backward so that no stream
             # operation sits between forward -> finalise -> backward (that would break their programmatic dependent
             # launches); it overlaps the next step's kernels, and this stream is ordered after the PREVIOUS collective.
-            comm.join(stream)
+            comm.join(stream, COMM_LAG)
             comm.allreduce_ptr(stats_ptrs[i % POOL], n_stats, stream)
 
     # ---- warm-up: at least W steps, and enough of them (~0.2 s) for the clocks to be up.  The count is FIXED, not

@@ -264,13 +264,13 @@ int msq_tune_set(const char* key, int value);
  * hands the 128 bytes to the other ranks (any transport; the Python side uses a torch.distributed
  * broadcast); every rank then calls msq_comm_create (collective).  msq_comm_allreduce_f64 forks a
  * side stream from `stream`, so the collective overlaps whatever the caller enqueues next (the
- * backward kernel); msq_comm_join makes `stream` wait for it.  libnccl.so.2 is dlopen'ed.
+ * backward kernel); msq_comm_join makes `stream` wait for the collective issued `lag` calls ago.  libnccl.so.2 is dlopen'ed.
  * ------------------------------------------------------------------------- */
 typedef struct msq_comm msq_comm;
 int msq_comm_unique_id(void* id128 /* host, 128 bytes */);
 int msq_comm_create(const void* id128, int world, int rank, msq_comm** out);
 int msq_comm_allreduce_f64(msq_comm* comm, double* buf /* device, in place */, int count, msq_stream_t stream);
-int msq_comm_join(msq_comm* comm, msq_stream_t stream);
+int msq_comm_join(msq_comm* comm, int lag /* 0 = most recent all-reduce, k = k calls earlier (< 8) */, msq_stream_t stream);
 void msq_comm_destroy(msq_comm* comm);
 
 #ifdef __cplusplus

@@ -97,7 +97,7 @@ def load():
         lib.msq_comm_allreduce_f64.restype = i32
         lib.msq_comm_allreduce_f64.argtypes = [vp, vp, i32, vp]
         lib.msq_comm_join.restype = i32
-        lib.msq_comm_join.argtypes = [vp, vp]
+        lib.msq_comm_join.argtypes = [vp, i32, vp]
         lib.msq_comm_destroy.restype = None
         lib.msq_comm_destroy.argtypes = [vp]
         lib.msq_pipe_destroy.restype = None

@@ -49,15 +49,16 @@ const NcclApi& nccl() {
 }
 
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;      // nccl.h: ncclDataType_t / ncclRedOp_t
+constexpr int kRing = 8;
 
 }  // namespace
 
 struct msq_comm {
     nccl_comm_t comm;
     cudaStream_t side;
-    cudaEvent_t fork, done;
+    cudaEvent_t fork, done[kRing];        // done[n % kRing]: completion of the n-th all-reduce
     int world, rank;
-    bool pending;
+    unsigned long long issued;
 };
 
 extern "C" int msq_comm_unique_id(void* id128) {
@@ -71,15 +72,17 @@ extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm*
     if (!nccl().ok) return MSQ_E_NCCL;
     msq_comm* c = new (std::nothrow) msq_comm();
     if (!c) return (int)cudaErrorMemoryAllocation;
-    c->world = world; c->rank = rank; c->pending = false;
+    c->world = world; c->rank = rank; c->issued = 0;
     nccl_unique_id id;
     memcpy(&id, id128, sizeof(id));
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return (int)e; }
     cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+    for (int i = 0; i < kRing; ++i) cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
     if (nccl().comm_init_rank(&c->comm, world, id, rank) != 0) {
-        cudaEventDestroy(c->fork); cudaEventDestroy(c->done); cudaStreamDestroy(c->side);
+        cudaEventDestroy(c->fork);
+        for (int i = 0; i < kRing; ++i) cudaEventDestroy(c->done[i]);
+        cudaStreamDestroy(c->side);
         delete c;
         return MSQ_E_NCCL;
     }
@@ -95,16 +98,18 @@ extern "C" int msq_comm_allreduce_f64(msq_comm* c, double* buf, int count, msq_s
     if ((e = cudaEventRecord(c->fork, (cudaStream_t)stream)) != cudaSuccess) return (int)e;
     if ((e = cudaStreamWaitEvent(c->side, c->fork, 0)) != cudaSuccess) return (int)e;
     if (nccl().all_reduce(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->side) != 0) return MSQ_E_NCCL;
-    if ((e = cudaEventRecord(c->done, c->side)) != cudaSuccess) return (int)e;
-    c->pending = true;
+    if ((e = cudaEventRecord(c->done[c->issued % kRing], c->side)) != cudaSuccess) return (int)e;
+    c->issued++;
     return 0;
 }
 
-// Make `stream` wait for the most recent all-reduce (no host synchronisation).
-extern "C" int msq_comm_join(msq_comm* c, msq_stream_t stream) {
-    if (!c) return MSQ_E_BADARG;
-    if (!c->pending) return 0;
-    const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, c->done, 0);
+// Make `stream` wait for the all-reduce issued `lag` calls before the most recent one (lag 0 = the most
+// recent; no host synchronisation).  A lag of 1-2 lets a collective take more than one step without stalling
+// the kernels: the statistics it carries are only logged.
+extern "C" int msq_comm_join(msq_comm* c, int lag, msq_stream_t stream) {
+    if (!c || lag < 0 || lag >= kRing) return MSQ_E_BADARG;
+    if (c->issued <= (unsigned long long)lag) return 0;
+    const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, c->done[(c->issued - 1 - lag) % kRing], 0);
     return (int)e;
 }
 
@@ -113,7 +118,7 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
     cudaStreamSynchronize(c->side);
     if (c->comm) nccl().comm_destroy(c->comm);
     cudaEventDestroy(c->fork);
-    cudaEventDestroy(c->done);
+    for (int i = 0; i < kRing; ++i) cudaEventDestroy(c->done[i]);
     cudaStreamDestroy(c->side);
     delete c;
 }

@@ -101,11 +101,14 @@ class StatsComm:
         if rc:
             self._libmod.check(rc)
 
-    def join(self, stream=None):
-        """Make the current stream wait for the most recent ``allreduce`` (no host synchronisation)."""
+    def join(self, stream=None, lag=0):
+        """Make the current stream wait for the ``allreduce`` issued ``lag`` calls before the most recent one
+        (0 = the most recent); no host synchronisation."""
         if stream is None:
             stream = torch.cuda.current_stream().cuda_stream
-        self._libmod.check(self._lib.msq_comm_join(self._h, stream))
+        rc = self._lib.msq_comm_join(self._h, int(lag), stream)
+        if rc:
+            self._libmod.check(rc)
 
     def close(self):
         if getattr(self, "_h", None):
