@@ -255,15 +255,17 @@ def run_b200(args, rank, world, local_rank):
     stats_ptrs = [v.data_ptr() for v in stats_views]
     n_stats = 1 + C
 
+    comm_h = comm._h if comm is not None else None
+
     def step(i):
-        fwd(i)
-        bwd(i)
-        if world > 1:
-            # one small all-reduce per step (NCCL, side stream).  It is forked AFTER the backward so that no stream
-            # operation sits between forward -> finalise -> backward (that would break their programmatic dependent
-            # launches); it overlaps the next step's kernels, and this stream is ordered after the PREVIOUS collective.
-            comm.join(stream, COMM_LAG)
-            comm.allreduce_ptr(stats_ptrs[i % POOL], n_stats, stream)
+        # ONE library call per step (C ABI msq_fused_fwd_bwd): fused forward, finalise, backward and -- when sharded --
+        # the statistics all-reduce (NCCL, side stream), forked AFTER the backward so that no stream operation sits
+        # between forward -> finalise -> backward (that would break their programmatic dependent launches)
+        j = i % POOL
+        rc = lib.msq_fused_fwd_bwd(MODE, lo_ptrs[j], N_IMG, C, h, w, H, W, RATIO, n_norm, acc_ptr, out_ptrs[j],
+                                   aux_ptrs[i % AUX_POOL], go_ptr, 0.0, gr_ptrs[j], comm_h, COMM_LAG, stream)
+        if rc:
+            _lib.check(rc)
 
     # ---- warm-up: at least W steps, and enough of them (~0.2 s) for the clocks to be up.  The count is FIXED, not
     #      time-based: every rank must issue the same number of all-reduces

@@ -273,6 +273,15 @@ int msq_comm_allreduce_f64(msq_comm* comm, double* buf /* device, in place */, i
 int msq_comm_join(msq_comm* comm, int lag /* 0 = most recent all-reduce, k = k calls earlier (< 8) */, msq_stream_t stream);
 void msq_comm_destroy(msq_comm* comm);
 
+/* One library call per training step: msq_fused_fwd + msq_fused_bwd (+ the statistics all-reduce of out.stats when
+ * comm != NULL, forked after the backward and ordered after the collective issued `lag` steps earlier), for callers
+ * that know the upstream gradient when they call the forward -- lambda_target is a constant
+ * (tools/solve_gta5.py:199,217).  grad = *grad_out (device scalar) if grad_out != NULL, else grad_scale. */
+int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                      double ratio, int n_images_norm, void* accum, void* out, void* aux /* nullable */,
+                      const float* grad_out /* nullable */, float grad_scale, float* grad_logits,
+                      msq_comm* comm /* nullable */, int lag, msq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ MODE_IW = 1
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
            "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
-           "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_join", "msq_comm_destroy",
+           "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_join", "msq_comm_destroy",
            "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
@@ -90,6 +90,8 @@ def load():
         lib.msq_pipe_wait.argtypes = [vp, i32]
         lib.msq_pipe_drain.restype = i32
         lib.msq_pipe_drain.argtypes = [vp]
+        lib.msq_fused_fwd_bwd.restype = i32
+        lib.msq_fused_fwd_bwd.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp, vp, c.c_float, vp, vp, i32, vp]
         lib.msq_comm_unique_id.restype = i32
         lib.msq_comm_unique_id.argtypes = [vp]
         lib.msq_comm_create.restype = i32

@@ -122,3 +122,26 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
     cudaStreamDestroy(c->side);
     delete c;
 }
+
+// One call per training step for callers that know the upstream gradient scale when they call the forward
+// (lambda_target is a constant, tools/solve_gta5.py:199,217): msq_fused_fwd + msq_fused_bwd and, when the images are
+// sharded over ranks (comm != NULL), the step's statistics all-reduce -- forked after the backward so that nothing
+// sits between forward -> finalise -> backward, and ordered after the collective issued `lag` steps earlier.  Same
+// kernels and results as the separate calls; it exists to keep the host side of a 35 us step to one library call.
+extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
+                                 double ratio, int n_images_norm, void* accum, void* out, void* aux, const float* grad_out,
+                                 float grad_scale, float* grad_logits, msq_comm* comm, int lag, msq_stream_t stream) {
+    if (!grad_logits) return MSQ_E_BADARG;
+    if ((((uintptr_t)aux) & 15u) || (((uintptr_t)grad_logits) & 3u)) return MSQ_E_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum, out,
+                                     aux, grad_logits, s);
+    if (rc) return rc;
+    rc = msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
+                                 grad_logits, aux, 1, s);
+    if (rc || !comm) return rc;
+    rc = msq_comm_join(comm, lag, stream);
+    if (rc) return rc;
+    const msq_state_layout lay = msq::make_layout(n, num_class);
+    return msq_comm_allreduce_f64(comm, (double*)((char*)out + lay.stats_off), 1 + num_class, stream);
+}

@@ -337,3 +337,27 @@ def test_host_pipeline_matches_oracle(msq):
     ms.wait(ms.submit(lo.pin_memory(), loss, grad))
     assert abs(loss.item() - rl.item()) <= LOSS_RTOL * abs(rl.item())
     _grad_close(grad, rg)
+
+
+def test_one_call_step_equals_forward_plus_backward(msq):
+    """C ABI msq_fused_fwd_bwd (one library call per step) == the nn.Module's forward + backward."""
+    from maxsquareloss_b200 import _lib
+    lib = _lib.load()
+    for kind, mode in (("iw", _lib.MODE_IW), ("ms", _lib.MODE_MAXSQUARE)):
+        lo = synth.head_logits(2, 19, (33, 65), 12, 4.0).cuda()
+        x = lo.clone().requires_grad_(True)
+        crit = _crit(msq, kind, 19)
+        loss = crit(x, out_size=(257, 513))
+        (0.1 * loss).backward()
+        lay = _lib.state_layout(2, 19)
+        accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device="cuda")
+        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device="cuda")
+        aux = torch.empty(lib.msq_fused_aux_bytes(2, 257, 513), dtype=torch.uint8, device="cuda")
+        grad = torch.full_like(lo, float("nan"))
+        st = torch.cuda.current_stream().cuda_stream
+        for a in (aux.data_ptr(), None):              # with and without the statistics cache
+            _lib.check(lib.msq_fused_fwd_bwd(mode, lo.data_ptr(), 2, 19, 33, 65, 257, 513, 0.2, 0, accum.data_ptr(), out.data_ptr(),
+                                             a, None, 0.1, grad.data_ptr(), None, 0, st))
+            got = out[lay.loss_off:lay.loss_off + 4].view(torch.float32).item()
+            assert got == loss.item()
+            _grad_close(grad, x.grad, rtol=1e-5)
