@@ -53,3 +53,13 @@ sf0 = lambda i: lib.msq_source_ce_fwd(los[i % POOL].data_ptr(), ys[i % 4].data_p
 sb = lambda i: lib.msq_guidance_bwd(los[i % POOL].data_ptr(), N, C, hs, ws, Hs, Ws, out.data_ptr(), auxs[i % 4].data_ptr(), go.data_ptr(),
                                     gs[i % POOL].data_ptr(), 1, st)
 print(f"source N={N}: fwd(+cm) {timeit(sf):.1f} fwd(no cm) {timeit(sf0):.1f} bwd {timeit(sb):.1f} us  ({N*Hs*Ws/1e6:.2f} Mpx)", flush=True)
+
+# flip-ensemble evaluation kernel
+Hf, Wf = 512, 1024
+fa = [torch.randn(N, C, Hf, Wf, device=dev) * 3 for _ in range(2)]
+fb = [torch.flip(a, dims=[-1]) + torch.randn_like(a) for a in fa]
+gtf = [synth.blocky_labels(N, (Hf, Wf), C, 300 + i).to(dev) for i in range(2)]
+ff = lambda i: lib.msq_confusion_flip_f32(gtf[i % 2].data_ptr(), fa[i % 2].data_ptr(), fb[i % 2].data_ptr(), N, C, Hf, Wf, cm.data_ptr(), st)
+t = timeit(ff, 100, 10)
+byt = (8.0 * C + 8) * N * Hf * Wf
+print(f"flip N={N}: {t:.1f} us  {byt / t / 1e3:.0f} GB/s = {byt / t / 1e3 / 6533.8 * 100:.0f}% of HBM", flush=True)
