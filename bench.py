@@ -309,7 +309,7 @@ def run_b200(args, rank, world, local_rank):
     #      and dL/dlogits back to the host; `depth` steps in flight so copies overlap kernels.
     e2e_pool = min(POOL, 16)
     host_in = [lo_pool[i].cpu().pin_memory() for i in range(e2e_pool)]
-    depth = int(os.environ.get("MSQ_BENCH_DEPTH", "8"))          # a step is ~100 us of latency end to end (H2D, kernels, D2H)
+    depth = int(os.environ.get("MSQ_BENCH_DEPTH", "16"))         # a step is ~100 us of latency end to end (H2D, kernels, D2H)
     pipe = msq.HostPipeline("iw", N_IMG, C, HW_LO, HW_OUT, ratio=RATIO, depth=depth)
     h_grad = [torch.empty(N_IMG, C, *HW_LO).pin_memory() for _ in range(depth)]
     h_loss = [torch.empty(()).pin_memory() for _ in range(depth)]
@@ -424,7 +424,7 @@ def run_b200(args, rank, world, local_rank):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lo_bytes),
                         "d2h_bytes_per_step": int(lo_bytes) + 4, "steps": e2e_steps,
                         "ms_per_step": e2e_s / e2e_steps * 1e3,
-                        "how": "HostPipeline.submit -> C ABI msq_pipe_submit: per step pinned host logits H2D, fused "
+                        "how": "HostPipeline.submit -> C ABI msq_pipe_submit (3-stream software pipeline): per step pinned host logits H2D, fused "
                                f"fwd+bwd, loss + dL/dlogits D2H; {depth} steps in flight, host waits on step i-{depth} "
                                "before reusing its buffers", "last_loss": last_loss,
                         "autograd_per_rank": {"value": ag_val, "unit": UNIT, "steps": ag_steps,

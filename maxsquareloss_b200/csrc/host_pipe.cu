@@ -1,7 +1,10 @@
 // Host-buffer pipeline: the fused loss step (H2D of the head logits, forward, finalise,
 // backward, D2H of the loss / histogram / dL/dlogits) for callers whose tensors live in
-// HOST memory, with `depth` submissions in flight on separate streams so that the copies
-// of one step overlap the kernels of another.  This is the non-PyTorch way into the hot
+// HOST memory, software-pipelined over THREE streams -- host->device copies, kernels, device->host
+// copies -- with `depth` submissions (slots of device buffers) in flight: the kernels of all steps
+// run back to back on one stream exactly as in the device-resident loop (their programmatic
+// dependent launches intact, no two one-wave grids competing for the SMs), while the copy engines
+// work on the neighbouring steps.  This is the non-PyTorch way into the hot
 // path (tools/solve_gta5.py:366-371,199,217 do the same sequence with torch ops: x.to(device),
 // model head, loss, backward, .item()).
 #include <new>
@@ -14,9 +17,9 @@ struct msq_pipe {
     double ratio;
     size_t lo_bytes;
     msq_state_layout lay;
+    cudaStream_t s_h2d, s_comp, s_d2h;
     struct Slot {
-        cudaStream_t stream;
-        cudaEvent_t done;
+        cudaEvent_t staged, computed, done;      // input on the device / kernels finished / outputs on the host
         float* d_logits;
         float* d_grad;
         unsigned char* d_accum;
@@ -29,20 +32,26 @@ struct msq_pipe {
 
 static void pipe_free(msq_pipe* p) {
     if (!p) return;
+    if (p->s_h2d) cudaStreamSynchronize(p->s_h2d);
+    if (p->s_comp) cudaStreamSynchronize(p->s_comp);
+    if (p->s_d2h) cudaStreamSynchronize(p->s_d2h);
     if (p->slots) {
         for (int i = 0; i < p->depth; ++i) {
             msq_pipe::Slot& s = p->slots[i];
-            if (s.stream) cudaStreamSynchronize(s.stream);
             if (s.d_logits) cudaFree(s.d_logits);
             if (s.d_grad) cudaFree(s.d_grad);
             if (s.d_accum) cudaFree(s.d_accum);
             if (s.d_out) cudaFree(s.d_out);
             if (s.d_aux) cudaFree(s.d_aux);
+            if (s.staged) cudaEventDestroy(s.staged);
+            if (s.computed) cudaEventDestroy(s.computed);
             if (s.done) cudaEventDestroy(s.done);
-            if (s.stream) cudaStreamDestroy(s.stream);
         }
         delete[] p->slots;
     }
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+    if (p->s_comp) cudaStreamDestroy(p->s_comp);
+    if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
     delete p;
 }
 
@@ -61,16 +70,20 @@ extern "C" int msq_pipe_create(int mode, int n, int num_class, int h, int w, int
     p->slots = new (std::nothrow) msq_pipe::Slot[depth]();
     if (!p->slots) { delete p; return (int)cudaErrorMemoryAllocation; }
     cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking);
     for (int i = 0; i < depth && e == cudaSuccess; ++i) {
         msq_pipe::Slot& s = p->slots[i];
-        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming)) != cudaSuccess) break;
         if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_logits, p->lo_bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_grad, p->lo_bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_accum, (size_t)p->lay.accum_bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_out, (size_t)p->lay.out_bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&s.d_aux, (size_t)(16 * (long long)n * out_h * out_w))) != cudaSuccess) break;
-        if ((e = cudaMemsetAsync(s.d_accum, 0, (size_t)p->lay.accum_bytes, s.stream)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s.d_accum, 0, (size_t)p->lay.accum_bytes, p->s_comp)) != cudaSuccess) break;
     }
     if (e != cudaSuccess) { pipe_free(p); return (int)e; }
     *out = p;
@@ -98,23 +111,30 @@ extern "C" int msq_pipe_submit(msq_pipe* p, const float* host_logits, float grad
     int rc = msq_pipe_wait(p, slot);
     if (rc) return rc;
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(s.d_logits, host_logits, p->lo_bytes, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) return (int)e;
+    // stage 1 (copy engine): input -> device.  The slot's buffers are free: the host waited for its last `done`.
+    if ((e = cudaMemcpyAsync(s.d_logits, host_logits, p->lo_bytes, cudaMemcpyHostToDevice, p->s_h2d)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventRecord(s.staged, p->s_h2d)) != cudaSuccess) return (int)e;
+    // stage 2 (SMs): all steps' kernels in submission order on one stream
+    if ((e = cudaStreamWaitEvent(p->s_comp, s.staged, 0)) != cudaSuccess) return (int)e;
     rc = fused_fwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, nullptr, p->ratio, 0, s.d_accum,
-                            s.d_out, host_grad ? s.d_aux : nullptr, host_grad ? s.d_grad : nullptr, s.stream);
+                            s.d_out, host_grad ? s.d_aux : nullptr, host_grad ? s.d_grad : nullptr, p->s_comp);
     if (rc) return rc;
     if (host_grad) {
         rc = fused_bwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, 0, s.d_out, nullptr, grad_scale,
-                                s.d_grad, s.d_aux, 1, s.stream);
+                                s.d_grad, s.d_aux, 1, p->s_comp);
         if (rc) return rc;
-        if ((e = cudaMemcpyAsync(host_grad, s.d_grad, p->lo_bytes, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return (int)e;
     }
-    if ((e = cudaMemcpyAsync(host_loss, s.d_out + p->lay.loss_off, sizeof(float), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventRecord(s.computed, p->s_comp)) != cudaSuccess) return (int)e;
+    // stage 3 (the other copy engine): outputs -> host
+    if ((e = cudaStreamWaitEvent(p->s_d2h, s.computed, 0)) != cudaSuccess) return (int)e;
+    if (host_grad && (e = cudaMemcpyAsync(host_grad, s.d_grad, p->lo_bytes, cudaMemcpyDeviceToHost, p->s_d2h)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpyAsync(host_loss, s.d_out + p->lay.loss_off, sizeof(float), cudaMemcpyDeviceToHost, p->s_d2h)) != cudaSuccess) return (int)e;
     if (host_hist) {
         e = cudaMemcpyAsync(host_hist, s.d_out + p->lay.hist_out_off, (size_t)p->n * p->C * sizeof(int32_t),
-                            cudaMemcpyDeviceToHost, s.stream);
+                            cudaMemcpyDeviceToHost, p->s_d2h);
         if (e != cudaSuccess) return (int)e;
     }
-    if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventRecord(s.done, p->s_d2h)) != cudaSuccess) return (int)e;
     s.busy = true;
     p->submitted++;
     if (slot_out) *slot_out = slot;
