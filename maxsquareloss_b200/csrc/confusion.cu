@@ -104,6 +104,8 @@ confusion_i64_kernel(const int64_t* __restrict__ gt, const int64_t* __restrict__
     for (int b = threadIdx.x; b < nbins * kConfSub; b += blockDim.x) s_all[b] = 0u;
     unsigned* s_cm = s_all + (threadIdx.x >> 8) * nbins;       // this warp group's sub-histogram
     __syncthreads();
+    pdl_trigger();          // programmatic dependent launch: the next kernel's shared-memory set-up may overlap our tail
+    pdl_wait();             // ... and ours overlapped the previous kernel's; global memory is touched from here on
 
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gstride = (long long)gridDim.x * blockDim.x;
@@ -162,6 +164,8 @@ confusion_logits_kernel(const int64_t* __restrict__ gt, const float* __restrict_
     const int nbins = C * C;
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_cm[b] = 0u;
     __syncthreads();
+    pdl_trigger();
+    pdl_wait();
 
     const int n = blockIdx.y;
     const int64_t* gt_n = gt + (long long)n * hw;
@@ -250,8 +254,10 @@ static int launch_i64(const int64_t* gt, const int64_t* pred, long long npix, in
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const size_t smem = (size_t)C * C * sizeof(unsigned) * kConfSub;
-    if (vec) confusion_i64_kernel<AGG, true><<<(unsigned)blocks, kConfBig, smem, st>>>(gt, pred, npix, C, cm, errs);
-    else confusion_i64_kernel<AGG, false><<<(unsigned)blocks, kConfBig, smem, st>>>(gt, pred, npix, C, cm, errs);
+    cudaError_t le;
+    if (vec) le = launch_pdl(confusion_i64_kernel<AGG, true>, dim3((unsigned)blocks), dim3(kConfBig), smem, st, gt, pred, npix, C, cm, errs);
+    else le = launch_pdl(confusion_i64_kernel<AGG, false>, dim3((unsigned)blocks), dim3(kConfBig), smem, st, gt, pred, npix, C, cm, errs);
+    if (le != cudaSuccess) return (int)le;
     MSQ_CHECK_LAUNCH();
     return 0;
 }
@@ -268,8 +274,10 @@ static int launch_logits(const int64_t* gt, const float* logits, int n, int C, l
     if (bx < 1) bx = 1;
     const dim3 grid((unsigned)bx, (unsigned)n);
     const size_t smem = (size_t)C * C * sizeof(unsigned);
-    if (vec) confusion_logits_kernel<CT, AGG, true><<<grid, kConfThreads, smem, st>>>(gt, logits, C, hw, cm);
-    else confusion_logits_kernel<0, AGG, false><<<grid, kConfThreads, smem, st>>>(gt, logits, C, hw, cm);
+    cudaError_t le;
+    if (vec) le = launch_pdl(confusion_logits_kernel<CT, AGG, true>, grid, dim3(kConfThreads), smem, st, gt, logits, C, hw, cm);
+    else le = launch_pdl(confusion_logits_kernel<0, AGG, false>, grid, dim3(kConfThreads), smem, st, gt, logits, C, hw, cm);
+    if (le != cudaSuccess) return (int)le;
     MSQ_CHECK_LAUNCH();
     return 0;
 }

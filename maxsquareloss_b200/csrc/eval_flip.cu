@@ -39,6 +39,8 @@ confusion_flip_kernel(const int64_t* __restrict__ gt, const float* __restrict__ 
     const int nbins = C * C;
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_cm[b] = 0u;
     __syncthreads();
+    pdl_trigger();          // programmatic dependent launch (see confusion.cu)
+    pdl_wait();
     const int n = blockIdx.y;
     const long long hw = (long long)H * W;
     const int64_t* gt_n = gt + (long long)n * hw;
@@ -116,8 +118,9 @@ static int launch_flip(const int64_t* gt, const float* la, const float* lb, int 
     const long long cap = ((long long)kSMs * 2 * 4 + n - 1) / n;      // a few waves over all images
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    confusion_flip_kernel<CT><<<dim3((unsigned)bx, (unsigned)n), kFlipThreads, (size_t)C * C * sizeof(unsigned), st>>>(
-        gt, la, lb, C, H, W, cm);
+    const cudaError_t le = launch_pdl(confusion_flip_kernel<CT>, dim3((unsigned)bx, (unsigned)n), dim3(kFlipThreads),
+                                      (size_t)C * C * sizeof(unsigned), st, gt, la, lb, C, H, W, cm);
+    if (le != cudaSuccess) return (int)le;
     MSQ_CHECK_LAUNCH();
     return 0;
 }

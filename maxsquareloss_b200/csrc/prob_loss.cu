@@ -44,6 +44,7 @@ prob_fwd_kernel(const float* __restrict__ prob, int n_img, int C, long long hw, 
         if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
         if (HAS_LABEL) __syncthreads();
     }
+    pdl_wait();             // programmatic dependent launch: global memory is touched only from here on
 
     const int n = blockIdx.y;
     const int rep_off = (int)(blockIdx.x % kRep) * n_img * C;        // this CTA's accumulator replica
@@ -162,6 +163,8 @@ prob_bwd_kernel(const float* __restrict__ prob, int C, long long hw, float ignor
     __shared__ float s_w[MSQ_MAX_CLASSES];
     const int n = blockIdx.y;
     const int tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();             // programmatic dependent launch: only the launch itself overlaps the previous kernel
     const float go = *grad_out;
     float coef;
     if (IW) {
@@ -258,11 +261,15 @@ static int launch_fwd(const float* prob, int n, int C, long long hw, const int64
     if (vec) {
         auto k = prob_fwd_kernel<CT, IW, HAS_LABEL, true>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<stream_grid(hw, n, 4, CT > 0 ? 2 : 4), kProbThreads, smem, s>>>(prob, n, C, hw, label, ign, st);
+        const cudaError_t le = launch_pdl(k, stream_grid(hw, n, 4, CT > 0 ? 2 : 4), dim3(kProbThreads), smem, s, prob, n, C,
+                                          (long long)hw, label, ign, st);
+        if (le != cudaSuccess) return (int)le;
     } else {
         auto k = prob_fwd_kernel<0, IW, HAS_LABEL, false>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<stream_grid(hw, n, 1, 4), kProbThreads, smem, s>>>(prob, n, C, hw, label, ign, st);
+        const cudaError_t le = launch_pdl(k, stream_grid(hw, n, 1, 4), dim3(kProbThreads), smem, s, prob, n, C, (long long)hw,
+                                          label, ign, st);
+        if (le != cudaSuccess) return (int)le;
     }
     MSQ_CHECK_LAUNCH();
     return launch_finalize(st, IW ? MSQ_MODE_IW : MSQ_MODE_MAXSQUARE, n, C, r32, omr32, n_norm, 0ull, s);
@@ -273,11 +280,15 @@ static int launch_bwd(const float* prob, int n, int C, long long hw, float ign, 
                       const float* grad_out, float* grad, cudaStream_t s) {
     const bool vec = ((hw & 3) == 0) && aligned16(prob) && aligned16(grad);
     if (vec && CT > 0) {
-        prob_bwd_kernel<CT, IW, true><<<stream_grid(hw, n, 4, 2), kProbThreads, 0, s>>>(
-            prob, C, hw, ign, n, n_norm, st.weights, st.kept_out, grad_out, grad);
+        const cudaError_t le = launch_pdl(prob_bwd_kernel<CT, IW, true>, stream_grid(hw, n, 4, 2), dim3(kProbThreads), 0, s, prob, C,
+                                          (long long)hw, ign, n, n_norm, (const float*)st.weights,
+                                          (const unsigned long long*)st.kept_out, grad_out, grad);
+        if (le != cudaSuccess) return (int)le;
     } else {
-        prob_bwd_kernel<0, IW, false><<<stream_grid(hw, n, 1, 4), kProbThreads, 0, s>>>(
-            prob, C, hw, ign, n, n_norm, st.weights, st.kept_out, grad_out, grad);
+        const cudaError_t le = launch_pdl(prob_bwd_kernel<0, IW, false>, stream_grid(hw, n, 1, 4), dim3(kProbThreads), 0, s, prob, C,
+                                          (long long)hw, ign, n, n_norm, (const float*)st.weights,
+                                          (const unsigned long long*)st.kept_out, grad_out, grad);
+        if (le != cudaSuccess) return (int)le;
     }
     MSQ_CHECK_LAUNCH();
     return 0;
