@@ -251,7 +251,6 @@ def run_b200(args, rank, world, local_rank):
         if rc:
             _lib.check(rc)
 
-    pending = []
     COMM_LAG = int(os.environ.get("MSQ_COMM_LAG", "0"))
     comm = mdist.StatsComm() if world > 1 else None
     if world > 1:
@@ -278,9 +277,8 @@ def run_b200(args, rank, world, local_rank):
         step(i)
         if i % 256 == 255:
             torch.cuda.synchronize()
-    for wk in pending:
-        wk.wait()
-    pending.clear()
+    if comm is not None:
+        comm.join(stream)
     torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY `steps` steps, barrier + synchronize on both sides, max over ranks

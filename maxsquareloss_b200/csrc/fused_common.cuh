@@ -71,6 +71,12 @@ __device__ __noinline__ int resolve_ties(const float* z, float m) {
 // lane (c & 1) of pair (c >> 1); an odd class count leaves one padding lane.
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float lane_of(const float2& v, int c) { return (c & 1) ? v.y : v.x; }
+// 2^t for the two classes of pair p.  With an odd class count the last pair's second lane is padding (logit -1e30,
+// exponential 0): no MUFU is spent on it (the kernels are MUFU co-limited: 20 -> 19 ex2 per pixel at C = 19).
+template <int CT>
+__device__ __forceinline__ float2 ex2_pair(const float2& t, int p) {
+    return make_float2(ex2_approx(t.x), (2 * p + 1 < CT) ? ex2_approx(t.y) : 0.f);
+}
 
 // Per-pixel softmax statistics from the interpolated logits z[] (pairs):
 //   e[c] = 2^((z_c - m) log2 e), inv_s = 1/s with s = sum e, q = sum_c p_c^2, qs = q*s;
@@ -112,7 +118,7 @@ __device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], floa
 #pragma unroll
     for (int p = 0; p < CP; ++p) {
         const float2 t = __ffma2_rn(z[p], l2e, nm);
-        e[p] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        e[p] = ex2_pair<CT>(t, p);
         if (p & 1) { s2b = __fadd2_rn(s2b, e[p]); ss2b = __ffma2_rn(e[p], e[p], ss2b); }
         else { s2a = __fadd2_rn(s2a, e[p]); ss2a = __ffma2_rn(e[p], e[p], ss2a); }
     }
@@ -158,7 +164,7 @@ __device__ __forceinline__ int pixel_stats_entropy(const float2 (&z)[(CT + 1) / 
     for (int p = 0; p < CP; ++p) {
         const float2 t = __fadd2_rn(z[p], nm2);
         const float2 tl = __fmul2_rn(t, l2e);
-        const float2 e = make_float2(ex2_approx(tl.x), ex2_approx(tl.y));
+        const float2 e = ex2_pair<CT>(tl, p);
         // padded lanes: t = -1e30, e = 0 exactly; keep 0 * -1e30 out of the sum
         const float2 tc = make_float2(fmaxf(t.x, -1.0e4f), fmaxf(t.y, -1.0e4f));
         if (p & 1) { sb = __fadd2_rn(sb, e); ab = __ffma2_rn(e, tc, ab); }
@@ -655,7 +661,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                 for (int p = 0; p < CP; ++p) {
                     const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
                     const float2 t = __ffma2_rn(zp, l2e, nm);
-                    const float2 ep = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    const float2 ep = ex2_pair<CT>(t, p);
                     const float2 noh = make_float2(labf == (float)(2 * p) ? -1.f : 0.f, labf == (float)(2 * p + 1) ? -1.f : 0.f);
                     const float2 v = __ffma2_rn(ep, is, noh);
                     dHa[p] = __ffma2_rn(a0, v, dHa[p]);
@@ -671,7 +677,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                     const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
                     const float2 t = __fadd2_rn(zp, nm2);
                     const float2 tl = __fmul2_rn(t, l2e);
-                    const float2 ep = make_float2(ex2_approx(tl.x), ex2_approx(tl.y));
+                    const float2 ep = ex2_pair<CT>(tl, p);
                     const float2 tc = make_float2(fmaxf(t.x, -1.0e4f), fmaxf(t.y, -1.0e4f));
                     const float2 v = __fmul2_rn(ep, __fadd2_rn(tc, nD));
                     dHa[p] = __ffma2_rn(a0, v, dHa[p]);
@@ -687,7 +693,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                 for (int p = 0; p < CP; ++p) {
                     const float2 zp = __ffma2_rn(Ha[p], w0, __fmul2_rn(Hb[p], w1));
                     const float2 t = __ffma2_rn(zp, l2e, nm);
-                    const float2 ep = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    const float2 ep = ex2_pair<CT>(t, p);
                     const float2 v = __fmul2_rn(ep, __fadd2_rn(ep, nqs));
                     dHa[p] = __ffma2_rn(a0, v, dHa[p]);
                     dHb[p] = __ffma2_rn(a1, v, dHb[p]);

@@ -163,7 +163,7 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
 #pragma unroll
                 for (int p = 0; p < CP; ++p) {
                     const float2 t = __ffma2_rn(z2[p], l2e, nm);
-                    e2[p] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    e2[p] = ex2_pair<CT>(t, p);
                     if (p & 1) sb = __fadd2_rn(sb, e2[p]); else sa = __fadd2_rn(sa, e2[p]);
                 }
                 const float2 ss = __fadd2_rn(sa, sb);

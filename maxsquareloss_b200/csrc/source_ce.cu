@@ -124,7 +124,7 @@ source_ce_fwd_kernel(const float* __restrict__ lo, const int64_t* __restrict__ l
 #pragma unroll
                 for (int p = 0; p < CP; ++p) {
                     const float2 t = __ffma2_rn(z[p], l2e, nm);
-                    const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    const float2 e = ex2_pair<CT>(t, p);
                     if (p & 1) sb = __fadd2_rn(sb, e); else sa = __fadd2_rn(sa, e);
                 }
                 const float2 ss = __fadd2_rn(sa, sb);
