@@ -105,3 +105,33 @@ def test_product_does_not_import_the_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_new_rows_have_no_cpu_fallback_either():
+    import torch
+    import maxsquareloss_b200 as msq
+    lo = torch.randn(1, 19, 4, 4)
+    y = torch.zeros(1, 8, 8, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.softCrossEntropy()(lo, out_size=(8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.IWsoftCrossEntropy(-1, 19, 0.2)(lo, out_size=(8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.CrossEntropyLoss2d()(lo, y)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.MultiLevelTargetLoss(msq.IW_MaxSquareloss(-1, 19, 0.2))((lo, lo), (8, 8))
+    with pytest.raises(TypeError):
+        msq.MultiLevelTargetLoss(torch.nn.CrossEntropyLoss())
+    with pytest.raises(RuntimeError):
+        msq.CrossEntropyLoss2d(weight=torch.ones(19))
+
+
+def test_comm_entry_points_reject_bad_arguments(lib):
+    import ctypes
+    assert lib.msq_comm_unique_id(None) == -1
+    h = ctypes.c_void_p()
+    assert lib.msq_comm_create(None, 2, 0, ctypes.byref(h)) == -1
+    assert lib.msq_comm_create(b"\0" * 128, 2, 5, ctypes.byref(h)) == -1
+    assert lib.msq_comm_allreduce_f64(None, None, 1, None) == -1
+    assert lib.msq_comm_join(None, 0, None) == -1
+    assert lib.msq_error_string(-5).startswith(b"msq:")
