@@ -43,6 +43,8 @@ struct FusedGeo {
     int C, h, w, H, W;
     float sy, sx;        // (in-1)/(out-1) in fp32 (0 when out == 1)
     int R;               // output rows per strip
+    unsigned uq, ur;     // units = uq * grid + ur: CTA b owns [b*uq + b*ur/grid, (b+1)*uq + (b+1)*ur/grid)  (b*ur < 2^32)
+    unsigned zq, zr;     // the same split of the n*C*h*w elements of dL/dlogits that the forward zero-fills
     int fastx;           // every run of output columns sharing x0 (or x1) within a tile is <= kRun long
     int nrm, ncp;        // max low-res rows / cols any strip touches (tile pitch)
 };
@@ -333,15 +335,15 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     // whatever precedes this kernel in the stream; global memory is touched only from here on
     pdl_wait();
     if (zero_buf) {                                    // zero dL/dlogits for the backward's red.adds: no memset launch
-        const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
-        const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
+        const unsigned z0 = blockIdx.x * g.zq + blockIdx.x * g.zr / gridDim.x;
+        const unsigned z1 = (blockIdx.x + 1) * g.zq + (blockIdx.x + 1) * g.zr / gridDim.x;
         for (unsigned i = z0 + tid; i < z1; i += kTW) zero_buf[i] = 0.f;
     }
     float4* __restrict__ ax = (float4*)aux;
 
     // units < 2^31 (checked on the host): 32-bit divisions only
-    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
-    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    unsigned u = blockIdx.x * g.uq + blockIdx.x * g.ur / gridDim.x;   // = floor(b * units / grid) without a 64-bit division
+    const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gridDim.x;
     const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
     unsigned long long ms_acc = 0ull;
     bool bad = false;
@@ -504,8 +506,8 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     const float4* __restrict__ ax = (const float4*)aux;
 
     // units < 2^31 (checked on the host): 32-bit divisions only
-    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
-    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    unsigned u = blockIdx.x * g.uq + blockIdx.x * g.ur / gridDim.x;   // = floor(b * units / grid) without a 64-bit division
+    const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gridDim.x;
     const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
     int coef_img = -1;
     while (u < u_end) {
@@ -790,6 +792,9 @@ static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_p
     if (grid < 1) grid = 1;
     if (grid > p.units) grid = p.units;
     p.grid = (int)grid;
+    g.uq = (unsigned)(p.units / grid); g.ur = (unsigned)(p.units % grid);
+    const long long zc = (long long)n * C * h * w;
+    g.zq = (unsigned)(zc / grid); g.zr = (unsigned)(zc % grid);
     long long rmax = (p.units + grid - 1) / grid;
     if (rmax > H) rmax = H;
     g.R = (int)rmax;

@@ -69,8 +69,8 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
     init_tile_pad<CT>(s_tile2, g);
     pdl_wait();            // global memory is touched only from here on (see fused_fwd_kernel)
     {
-        const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
-        const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
+        const unsigned z0 = blockIdx.x * g.zq + blockIdx.x * g.zr / gridDim.x;
+        const unsigned z1 = (blockIdx.x + 1) * g.zq + (blockIdx.x + 1) * g.zr / gridDim.x;
         for (unsigned i = z0 + tid; i < z1; i += kTW) {
             if (zero1) zero1[i] = 0.f;
             if (zero2) zero2[i] = 0.f;
@@ -79,8 +79,8 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
     float4* __restrict__ ax1 = (float4*)aux1;
     float4* __restrict__ ax2 = (float4*)aux2;
 
-    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
-    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    unsigned u = blockIdx.x * g.uq + blockIdx.x * g.ur / gridDim.x;   // = floor(b * units / grid) without a 64-bit division
+    const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gridDim.x;
     const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
     unsigned long long ms_acc = 0ull, ce_acc = 0ull;
     unsigned nvalid = 0u;

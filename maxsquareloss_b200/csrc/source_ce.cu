@@ -36,14 +36,14 @@ source_ce_fwd_kernel(const float* __restrict__ lo, const int64_t* __restrict__ l
     if (cm) for (int i = tid; i < g.C * g.C; i += kTW) s_cm[i] = 0u;
     pdl_wait();            // global memory is touched only from here on (see fused_fwd_kernel)
     if (zero_buf) {
-        const unsigned z0 = (unsigned)((unsigned long long)blockIdx.x * zero_count / gridDim.x);
-        const unsigned z1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * zero_count / gridDim.x);
+        const unsigned z0 = blockIdx.x * g.zq + blockIdx.x * g.zr / gridDim.x;
+        const unsigned z1 = (blockIdx.x + 1) * g.zq + (blockIdx.x + 1) * g.zr / gridDim.x;
         for (unsigned i = z0 + tid; i < z1; i += kTW) zero_buf[i] = 0.f;
     }
     float4* __restrict__ ax = (float4*)aux;
 
-    unsigned u = (unsigned)((unsigned long long)blockIdx.x * units / gridDim.x);
-    const unsigned u_end = (unsigned)((unsigned long long)(blockIdx.x + 1) * units / gridDim.x);
+    unsigned u = blockIdx.x * g.uq + blockIdx.x * g.ur / gridDim.x;   // = floor(b * units / grid) without a 64-bit division
+    const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gridDim.x;
     const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
     unsigned long long ce_acc = 0ull;
     unsigned nvalid = 0u;
