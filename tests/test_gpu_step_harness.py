@@ -87,3 +87,63 @@ def test_adaptation_step_matches_reference_chain():
     opt = torch.optim.SGD(model.parameters(), lr=2.5e-4, momentum=0.9, weight_decay=5e-4)   # train_source.py:139-146
     opt.step()
     assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+def test_crosscity_step_with_deeplabv2_resnet101():
+    """BASELINE config 5 as written: random-init DeepLabv2-ResNet101 (harness/deeplabv2.py, the reference's topology;
+    cuDNN, out of scope), batch 1, 13 classes, 512x1024, seed 12345 (train_source.py:755); the step of
+    tools/solve_crosscity.py:165-249 without --multi: source CE + Eval.add_batch, target IW-MaxSquare (lambda 0.1).
+    Reference chain = the model's two F.interpolate calls + torch ops (oracle port of the losses); fused = the
+    low-resolution heads straight into CrossEntropyLoss2d / IW_MaxSquareloss."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import maxsquareloss_b200 as msq
+    from harness.deeplabv2 import DeepLabV2Harness, head_size
+    from oracle import eval_port, loss_port
+    C, HW = 13, (512, 1024)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False            # the reference is plain fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(12345)
+        model = DeepLabV2Harness(C).cuda().train()
+        xs = torch.randn(1, 3, *HW, device="cuda")
+        ys = synth.blocky_labels(1, HW, C, 5).cuda()
+        xt = torch.randn(1, 3, *HW, device="cuda")
+        lam_t = 0.1
+
+        model.zero_grad()
+        pred, _ = model(xs, upsample=True)
+        loss_src = F.cross_entropy(pred, ys, ignore_index=-1)
+        loss_src.backward()
+        port = eval_port.EvalPort(C)
+        port.add_batch(ys.cpu().numpy(), np.argmax(pred.data.cpu().numpy(), axis=1))
+        tp, _ = model(xt, upsample=True)
+        loss_t = lam_t * loss_port.iw_maxsquare(F.softmax(tp, 1), C, 0.2)
+        loss_t.backward()
+        ref_grads = _param_grads_req(model)
+        ref_vals = (loss_src.item(), loss_t.item())
+
+        model.zero_grad()
+        ev = msq.Eval(C)
+        lo, _ = model(xs)
+        assert tuple(lo.shape[2:]) == head_size(*HW) == (65, 129)
+        f_src = msq.CrossEntropyLoss2d(ignore_index=-1)(lo, ys, evaluator=ev)
+        f_src.backward()
+        lt, _ = model(xt)
+        f_t = lam_t * msq.IW_MaxSquareloss(-1, C, 0.2)(lt, out_size=HW)
+        f_t.backward()
+        got_grads = _param_grads_req(model)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+    for a, b in zip((f_src.item(), f_t.item()), ref_vals):
+        assert abs(a - b) <= 1e-5 * abs(b)
+    assert (got_grads - ref_grads).abs().max().item() <= 1e-4 * ref_grads.abs().max().item()
+    assert (got_grads - ref_grads).norm().item() <= 1e-4 * ref_grads.norm().item()
+    assert np.array_equal(ev.confusion_matrix, port.confusion_matrix)
+    assert ev.Mean_Intersection_over_Union() == port.Mean_Intersection_over_Union()
+
+
+def _param_grads_req(model):
+    return torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad and p.grad is not None]).double()
