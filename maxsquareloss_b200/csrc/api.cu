@@ -15,17 +15,22 @@ namespace msq {
 // one warp per image, one lane per class (C <= 32)
 __global__ void __launch_bounds__(256)
 finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_norm, unsigned long long kept_dense,
-                int multi, int loss_kind) {
+                int multi, int loss_kind, const PeerBox box) {
     pdl_trigger();          // the backward may start its prologue now
     pdl_wait();             // ... but this kernel needs every forward CTA's atomics
+    if (blockIdx.x == 1) {  // sharded step: the statistics exchange over NVLink peer memory rides along (PeerBox, common.cuh)
+        if (threadIdx.x < 32) box_exchange(box.st, box.cur, box.prev_out, box.seq, box.count, box.prev_count, (int)threadIdx.x);
+        return;
+    }
     finalize_body(st, mode, n, C, r32, omr32, n_norm, kept_dense, multi, loss_kind);
 }
 
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                    unsigned long long kept_dense, cudaStream_t stream, int multi, int loss_kind) {
+                    unsigned long long kept_dense, cudaStream_t stream, int multi, int loss_kind, const PeerBox* box) {
     const int warps = n < 8 ? n : 8;
-    const cudaError_t e = launch_pdl(finalize_kernel, dim3(1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
-                                     n_norm, kept_dense, multi, loss_kind);
+    const PeerBox bx = box ? *box : PeerBox{};
+    const cudaError_t e = launch_pdl(finalize_kernel, dim3(bx.st ? 2 : 1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
+                                     n_norm, kept_dense, multi, loss_kind, bx);
     if (e != cudaSuccess) return (int)e;
     MSQ_CHECK_LAUNCH();
     return 0;

@@ -59,7 +59,35 @@ struct msq_comm {
     cudaEvent_t fork, done[kRing];        // done[n % kRing]: completion of the n-th all-reduce
     int world, rank;
     unsigned long long issued;
+    // peer-memory mailboxes (see PeerBox, common.cuh): used by msq_fused_fwd_bwd instead of ncclAllReduce
+    uint4* box_local;                     // this rank's mailbox (cudaMalloc)
+    uint4* box_peer[msq::kMaxPeers];      // every rank's mailbox as mapped here (box_peer[rank] == box_local)
+    unsigned* box_err;                    // device error word
+    msq::PeerBoxStatic* box_static;       // device copy of {world, rank, err, peers}
+    bool box_ready;
+    unsigned box_seq;                     // steps issued so far = sequence number of the newest vector
+    double* box_last;                     // statistics of step box_seq: produced, not pushed yet (NULL: none pending)
+    double* box_pushed;                   // statistics of step box_seq-1: pushed, not reduced yet (NULL: none pending)
+    int box_last_count, box_pushed_count;
 };
+
+namespace {
+constexpr size_t kBoxBytes = sizeof(uint4) * msq::kBoxSlots * msq::kMaxPeers * msq::kBoxCount;
+
+// completes the two steps still in flight (the steps themselves carry the exchange in their finalisation kernels):
+// pushes the newest vector, reduces the one before it, then reduces the newest in place
+__global__ void __launch_bounds__(32) box_flush_kernel(const msq::PeerBox box, double* last) {
+    msq::box_exchange(box.st, box.cur, box.prev_out, box.seq, box.count, box.prev_count, (int)threadIdx.x);
+    __syncwarp();
+    msq::box_reduce(box.st, box.seq, box.count, last, (int)threadIdx.x);
+}
+
+msq::PeerBox make_box(const msq_comm* c) {
+    msq::PeerBox b = {};
+    b.st = c->box_static;
+    return b;
+}
+}  // namespace
 
 extern "C" int msq_comm_unique_id(void* id128) {
     if (!id128) return MSQ_E_BADARG;
@@ -73,6 +101,8 @@ extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm*
     msq_comm* c = new (std::nothrow) msq_comm();
     if (!c) return (int)cudaErrorMemoryAllocation;
     c->world = world; c->rank = rank; c->issued = 0;
+    c->box_local = nullptr; c->box_err = nullptr; c->box_static = nullptr; c->box_ready = false; c->box_seq = 0u; c->box_last = nullptr; c->box_pushed = nullptr; c->box_last_count = 0; c->box_pushed_count = 0;
+    for (int p = 0; p < msq::kMaxPeers; ++p) c->box_peer[p] = nullptr;
     nccl_unique_id id;
     memcpy(&id, id128, sizeof(id));
     cudaError_t e;
@@ -108,14 +138,91 @@ extern "C" int msq_comm_allreduce_f64(msq_comm* c, double* buf, int count, msq_s
 // the kernels: the statistics it carries are only logged.
 extern "C" int msq_comm_join(msq_comm* c, int lag, msq_stream_t stream) {
     if (!c || lag < 0 || lag >= kRing) return MSQ_E_BADARG;
+    if (c->box_ready && c->box_last && lag == 0) {
+        // peer-memory path: the newest step's vector is not pushed yet, the one before it not reduced yet
+        msq::PeerBox b = make_box(c);
+        b.cur = c->box_last;
+        b.seq = c->box_seq;
+        b.count = (short)c->box_last_count;
+        b.prev_out = c->box_pushed;
+        b.prev_count = (short)c->box_pushed_count;
+        box_flush_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b, c->box_last);
+        c->box_last = nullptr;
+        c->box_pushed = nullptr;
+        MSQ_CHECK_LAUNCH();
+    }
     if (c->issued <= (unsigned long long)lag) return 0;
     const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, c->done[(c->issued - 1 - lag) % kRing], 0);
     return (int)e;
 }
 
+// ---- peer-memory mailboxes -------------------------------------------------------------------------------
+// msq_comm_box_export: allocate and zero this rank's mailbox, return its 64-byte cudaIpc handle.  The caller
+// all-gathers the handles (torch.distributed: plumbing) and hands all of them, in rank order, to msq_comm_box_open,
+// which maps the peers' mailboxes (NVLink peer access).  Both are collective over the ranks of the communicator; if
+// either fails on any rank the caller simply does not use the mailboxes (msq_fused_fwd_bwd then all-reduces with NCCL).
+extern "C" int msq_comm_box_export(msq_comm* c, void* handle64) {
+    if (!c || !handle64) return MSQ_E_BADARG;
+    if (c->world > msq::kMaxPeers) return MSQ_E_BADARG;
+    cudaError_t e;
+    if (!c->box_local) {
+        constexpr size_t kTail = 16 + sizeof(msq::PeerBoxStatic);
+        if ((e = cudaMalloc((void**)&c->box_local, kBoxBytes + kTail)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemset(c->box_local, 0, kBoxBytes + kTail)) != cudaSuccess) return (int)e;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
+        c->box_err = (unsigned*)((char*)c->box_local + kBoxBytes);
+        c->box_static = (msq::PeerBoxStatic*)((char*)c->box_local + kBoxBytes + 16);
+    }
+    cudaIpcMemHandle_t h;
+    if ((e = cudaIpcGetMemHandle(&h, c->box_local)) != cudaSuccess) return (int)e;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int msq_comm_box_open(msq_comm* c, const void* handles /* world x 64 bytes, rank order */) {
+    if (!c || !handles || !c->box_local || c->world > msq::kMaxPeers) return MSQ_E_BADARG;
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) { c->box_peer[p] = c->box_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * p, 64);
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+        c->box_peer[p] = (uint4*)ptr;
+    }
+    msq::PeerBoxStatic st = {};
+    st.world = c->world;
+    st.rank = c->rank;
+    st.err = c->box_err;
+    for (int p = 0; p < c->world; ++p) st.peer[p] = c->box_peer[p];
+    cudaError_t e = cudaMemcpy(c->box_static, &st, sizeof(st), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
+    c->box_ready = true;
+    return 0;
+}
+
+// 1 if msq_fused_fwd_bwd exchanges the statistics through the mailboxes, 0 if it uses ncclAllReduce
+extern "C" int msq_comm_box_active(const msq_comm* c) { return (c && c->box_ready) ? 1 : 0; }
+
+// device error word of the mailbox path (bit 0: a peer's vector never arrived); synchronises the device
+extern "C" int msq_comm_box_errors(msq_comm* c, unsigned* out) {
+    if (!c || !out) return MSQ_E_BADARG;
+    *out = 0u;
+    if (!c->box_err) return 0;
+    return (int)cudaMemcpy(out, c->box_err, sizeof(unsigned), cudaMemcpyDeviceToHost);
+}
+
 extern "C" void msq_comm_destroy(msq_comm* c) {
     if (!c) return;
     cudaStreamSynchronize(c->side);
+    if (c->box_local) {
+        cudaDeviceSynchronize();
+        for (int p = 0; p < c->world && p < msq::kMaxPeers; ++p)
+            if (p != c->rank && c->box_peer[p]) cudaIpcCloseMemHandle(c->box_peer[p]);
+        cudaFree(c->box_local);
+    }
     if (c->comm) nccl().comm_destroy(c->comm);
     cudaEventDestroy(c->fork);
     for (int i = 0; i < kRing; ++i) cudaEventDestroy(c->done[i]);
@@ -134,6 +241,32 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
     if (!grad_logits) return MSQ_E_BADARG;
     if ((((uintptr_t)aux) & 15u) || (((uintptr_t)grad_logits) & 3u)) return MSQ_E_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
+    const msq_state_layout lay = msq::make_layout(n, num_class);
+    double* stats = (double*)((char*)out + lay.stats_off);
+    if (comm && comm->box_ready && 1 + num_class <= msq::kBoxCount) {
+        // sharded: a second CTA of this step's finalisation kernel pushes the PREVIOUS step's [loss | hist] into every
+        // rank's mailbox over NVLink and reduces the step before that; nothing is enqueued between or after the three
+        // kernels of the step and the hot kernels are untouched
+        msq::PeerBox b = {};
+        if (comm->box_last) {
+            b = make_box(comm);
+            b.cur = comm->box_last;
+            b.seq = comm->box_seq;
+            b.count = (short)comm->box_last_count;
+            b.prev_out = comm->box_pushed;
+            b.prev_count = (short)comm->box_pushed_count;
+        }
+        int rc = msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum,
+                                         out, aux, grad_logits, s, 0, &b);
+        if (rc) return rc;
+        comm->box_pushed = comm->box_last;
+        comm->box_pushed_count = comm->box_last_count;
+        comm->box_last = stats;
+        comm->box_last_count = 1 + num_class;
+        comm->box_seq += 1u;
+        return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
+                                       grad_logits, aux, 1, s);
+    }
     int rc = msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum, out,
                                      aux, grad_logits, s);
     if (rc) return rc;
@@ -142,6 +275,5 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
     if (rc || !comm) return rc;
     rc = msq_comm_join(comm, lag, stream);
     if (rc) return rc;
-    const msq_state_layout lay = msq::make_layout(n, num_class);
-    return msq_comm_allreduce_f64(comm, (double*)((char*)out + lay.stats_off), 1 + num_class, stream);
+    return msq_comm_allreduce_f64(comm, stats, 1 + num_class, stream);
 }

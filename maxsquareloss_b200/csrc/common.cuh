@@ -252,6 +252,86 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
 }
 
 
+// ---- statistics exchange over NVLink peer memory (comm.cu) -----------------------------------------------
+// When the images are sharded over the GPUs of one box, the only data that crosses GPUs is the packed fp64
+// statistics vector [loss | class histogram] of each step (<= 264 bytes).  Instead of a collective library call
+// per step, the step's own finalisation kernel carries the exchange in a second CTA that runs beside the
+// finalisation proper: one warp PUSHES the vector this rank produced in the PREVIOUS step into every rank's mailbox
+// with 16-byte stores over NVLink (cudaIpc-mapped peer memory), then sums the vectors all ranks pushed one step
+// earlier still (they arrived a whole step ago) in rank order and writes that step's all-reduced result.  No
+// extra launch, no stream operation between the step's kernels (which would break their programmatic dependent
+// launches), no host cost, nothing added to the forward -> finalise -> backward critical path and not one
+// register to the hot kernels; the all-reduced vector of step i exists once the finalisation of step i+2 (or
+// msq_comm_join) has run.
+// Cells are NCCL-LL style {lo32, flag, hi32, flag}: data and flag travel in the same 8-byte store, so the
+// reader needs no fence: it polls until both flags carry the sequence number it expects.
+constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch box
+constexpr int kBoxSlots = 8;       // ring of sequence numbers; a writer is never more than 5 steps ahead of a reader
+constexpr int kBoxCount = 40;      // doubles per vector (1 + 32 classes, rounded up)
+constexpr unsigned kBoxSpinLimit = 1u << 22;     // polls before a cell is declared lost (~ seconds): never hang the GPU
+
+// Static part, resident in device memory (written once by msq_comm_box_open).
+struct PeerBoxStatic {
+    int world, rank;
+    unsigned* err;                 // local error word: bit 0 = a peer's cell never arrived
+    uint4* peer[kMaxPeers];        // rank p's mailbox: [kBoxSlots][kMaxPeers][kBoxCount] cells (peer[rank] is local)
+};
+// Per-step part, passed to the kernel by value (32 bytes of parameters; st == NULL: no exchange).
+struct PeerBox {
+    const PeerBoxStatic* st;
+    const double* cur;             // the vector to push: this rank's statistics of sequence number `seq` (NULL: none)
+    double* prev_out;              // where the all-reduced vector of sequence number seq-1 goes (NULL: nothing to reduce)
+    unsigned seq;                  // 1, 2, ...; 0 is never used (it is the flag value of an empty cell)
+    short count, prev_count;       // doubles in the pushed / the reduced vector
+};
+
+__device__ __forceinline__ void ll_store(uint4* cell, double v, unsigned flag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(cell), "r"((unsigned)b), "r"(flag), "r"((unsigned)(b >> 32)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4* cell, unsigned flag, double& v) {
+    unsigned a, fa, b, fb;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(cell) : "memory");
+    if (fa != flag || fb != flag) return false;
+    v = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+    return true;
+}
+__device__ __forceinline__ uint4* box_cell(uint4* base, unsigned seq, int src_rank, int k) {
+    return base + ((size_t)(seq % kBoxSlots) * kMaxPeers + src_rank) * kBoxCount + k;
+}
+// sum over the ranks, in rank order (identical bits on every rank), of the vectors pushed for `seq`
+__device__ __forceinline__ void box_reduce(const PeerBoxStatic* st, unsigned seq, int count, double* out, int lane) {
+    const int world = st->world, rank = st->rank;
+    uint4* mine = st->peer[rank];
+    bool lost = false;
+    for (int k = lane; k < count; k += 32) {
+        double sum = 0.0;
+        for (int p = 0; p < world; ++p) {
+            const uint4* cell = box_cell(mine, seq, p, k);
+            double v = 0.0;
+            unsigned spins = 0;
+            while (!ll_load(cell, seq, v)) {
+                if (lost || ++spins > kBoxSpinLimit) { lost = true; v = __longlong_as_double(0x7ff8000000000000LL); break; }
+                __nanosleep(64);
+            }
+            sum += v;
+        }
+        out[k] = sum;
+    }
+    if (lost) atomicOr(st->err, 1u);
+}
+// One warp: push vector `seq` to every rank (itself included), then reduce vector seq-1.
+__device__ __forceinline__ void box_exchange(const PeerBoxStatic* st, const double* cur, double* prev_out, unsigned seq,
+                                          int count, int prev_count, int lane) {
+    const int world = st->world, rank = st->rank;
+    for (int k = lane; cur && k < count; k += 32) {
+        const double v = cur[k];
+        for (int p = 0; p < world; ++p) ll_store(box_cell(st->peer[p], seq, rank, k), v, seq);
+    }
+    if (prev_out) box_reduce(st, seq - 1u, prev_count, prev_out, lane);
+}
+
 // Finalisation kernel (api.cu), launched on the same stream right after a forward kernel:
 // sums the replicas, turns the integer accumulators into the reference's scalar, the
 // per-image weights and the final histogram, and re-zeroes the accumulators so the
@@ -260,12 +340,13 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
 //   MaxSquare (utils/loss.py:118):     loss = -(sum q) / (2 * kept)
 // Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                    unsigned long long kept_dense, cudaStream_t stream, int multi = 0, int loss_kind = 0);
+                    unsigned long long kept_dense, cudaStream_t stream, int multi = 0, int loss_kind = 0,
+                    const PeerBox* box = nullptr);
 
 // fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
-                       float* zero_grad, cudaStream_t s, int loss_kind = 0);
+                       float* zero_grad, cudaStream_t s, int loss_kind = 0, const PeerBox* box = nullptr);
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
                        float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind = 0);

@@ -31,7 +31,8 @@ int g_reserve_sms = 0;
 
 template <int CT, bool PAD>
 static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, const int64_t* label,
-                            float r32, float omr32, int nn, State st, void* aux, float* zero_buf, cudaStream_t s, int loss_kind) {
+                            float r32, float omr32, int nn, State st, void* aux, float* zero_buf, cudaStream_t s, int loss_kind,
+                            const PeerBox* box) {
     const unsigned zero_count = zero_buf ? (unsigned)((size_t)n * C * h * w) : 0u;
     const bool iw = mode != MSQ_MODE_MAXSQUARE;
 #define MSQ_LAUNCH(K)                                                                          \
@@ -53,7 +54,7 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
     else MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, false>));
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
-    return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s, 0, loss_kind);
+    return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s, 0, loss_kind, box);
 }
 
 template <int CT, bool PAD>
@@ -108,7 +109,7 @@ namespace msq {
 
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
-                       float* zero_grad, cudaStream_t s, int loss_kind) {
+                       float* zero_grad, cudaStream_t s, int loss_kind, const PeerBox* box) {
     if (!logits || !accum || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES || h < 1 || w < 1 || out_h < 1 ||
         out_w < 1)
         return MSQ_E_BADARG;
@@ -117,7 +118,7 @@ int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int 
     const State st = carve(accum, out, n, num_class);
     const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s, loss_kind)
+#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s, loss_kind, box)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }

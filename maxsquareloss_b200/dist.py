@@ -14,6 +14,8 @@ over NCCL/NVLink (gloo in the CPU tests).  Counts below 2**53 are exact in
 fp64, so the integers come back bit-exact.  The dL/dlogits of a rank's images
 depends on nothing from other ranks, so the gradient path has no collective.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -67,9 +69,13 @@ class StatsComm:
     """The per-step all-reduce of the packed statistics vector, enqueued by libmsq_b200 on an NCCL communicator
     of its own (C ABI ``msq_comm_*``): one ``ncclAllReduce`` on a side stream per call and ~3 us of host time,
     against ~25 us for ``torch.distributed.all_reduce``.  ``torch.distributed`` is used once, to hand rank 0's
-    NCCL unique id to the other ranks.  CUDA only."""
+    NCCL unique id to the other ranks.  CUDA only.
 
-    def __init__(self, group=None):
+    With ``peer_memory`` (default, <= 8 ranks of one NVLink box) the one-call step ``msq_fused_fwd_bwd`` does not
+    call NCCL at all: its backward kernel pushes the vector into every rank's mailbox over NVLink and reduces the
+    previous step's (``include/msq_b200.h``, "Peer-memory mailboxes"); ``join()`` reduces the last pending step."""
+
+    def __init__(self, group=None, peer_memory=True):
         import ctypes
         from . import _lib
         if not (dist.is_available() and dist.is_initialized()):
@@ -88,6 +94,41 @@ class StatsComm:
         h = ctypes.c_void_p()
         _lib.check(self._lib.msq_comm_create(raw, self.world, self.rank, ctypes.byref(h)))
         self._h = h
+        self.peer_memory = False
+        if peer_memory and self.world <= 8 and os.environ.get("MSQ_PEERBOX", "1") != "0":
+            self._open_mailboxes(group, dev)
+
+    def _open_mailboxes(self, group, dev):
+        """NVLink peer-memory mailboxes for the per-step statistics (C ABI ``msq_comm_box_*``): every rank exports a
+        cudaIpc handle, the handles are all-gathered, every rank maps its peers.  Any failure on any rank (no peer
+        access, IPC not permitted in this container) leaves the communicator on NCCL."""
+        import ctypes
+        mine = ctypes.create_string_buffer(64)
+        ok = self._lib.msq_comm_box_export(self._h, mine) == 0
+        t = torch.zeros(65, dtype=torch.uint8)
+        if ok:
+            t[:64] = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8)
+            t[64] = 1
+        t = t.to(dev)
+        allh = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t, group=group)
+        allh = torch.stack(allh).cpu()
+        if not bool((allh[:, 64] == 1).all()):
+            return
+        blob = bytes(allh[:, :64].contiguous().numpy().tobytes())
+        rc = self._lib.msq_comm_box_open(self._h, blob)
+        flag = torch.tensor([1 if rc == 0 else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            raise RuntimeError("libmsq_b200: peer-memory mailboxes opened on some ranks only; set MSQ_PEERBOX=0")
+        self.peer_memory = bool(self._lib.msq_comm_box_active(self._h))
+
+    def errors(self):
+        """Error word of the mailbox path (0 = fine; bit 0 = a peer's vector never arrived).  Synchronises."""
+        import ctypes
+        v = ctypes.c_uint(0)
+        self._libmod.check(self._lib.msq_comm_box_errors(self._h, ctypes.byref(v)))
+        return int(v.value)
 
     def allreduce(self, buf):
         """Sum the float64 CUDA vector ``buf`` over the ranks, in place, asynchronously w.r.t. the current stream."""

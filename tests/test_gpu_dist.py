@@ -68,3 +68,66 @@ def test_stats_allreduce_two_ranks():
         assert abs(stats[0] - ref[0]) <= 1e-8 * abs(ref[0])              # loss: per-thread fp32 run sums depend on the row partition
         g = x.grad[a:b].cpu().numpy()
         assert np.abs(grad - g).max() <= 1e-5 * np.abs(g).max()          # no exchange needed for dL/dlogits
+
+
+def _worker_box(rank, world, port, q):
+    """One-call sharded steps with the statistics exchanged through the NVLink peer-memory mailboxes (the exchange rides in
+    the steps' finalisation kernels) and, for comparison, through ncclAllReduce on a second communicator."""
+    sys.path.insert(0, ROOT)
+    import datetime
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
+    from maxsquareloss_b200 import _lib, dist as mdist, synth
+    lib = _lib.load()
+    C, (h, w), (H, W), N, K = 19, (33, 65), (257, 513), 2, 13
+    lay = _lib.state_layout(N, C)
+    los = [synth.head_logits(N * world, C, (h, w), 100 + i, 4.0)[rank * N:(rank + 1) * N].cuda() for i in range(K)]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(comm, flush_at):
+        accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device="cuda")
+        outs = [torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda") for _ in range(K)]     # one per step in flight
+        aux = torch.empty(lib.msq_fused_aux_bytes(N, H, W), dtype=torch.uint8, device="cuda")
+        grad = torch.empty_like(los[0])
+        for i in range(K):
+            _lib.check(lib.msq_fused_fwd_bwd(_lib.MODE_IW, los[i].data_ptr(), N, C, h, w, H, W, 0.2, N * world, accum.data_ptr(),
+                                             outs[i].data_ptr(), aux.data_ptr(), None, 0.1, grad.data_ptr(), comm._h, 0, stream))
+            if i in flush_at:
+                comm.join()
+        comm.join()
+        torch.cuda.synchronize()
+        return np.stack([o[lay.stats_off:lay.stats_off + 8 * (1 + C)].view(torch.float64).cpu().numpy() for o in outs])
+
+    box, nccl = mdist.StatsComm(), mdist.StatsComm(peer_memory=False)
+    got = [run(box, ()), run(box, (0, 1, 6)), run(box, (K - 2,))]        # the communicator is reused; flushes anywhere
+    ref = run(nccl, ())
+    q.put((rank, box.peer_memory, nccl.peer_memory, box.errors(), got, ref))
+    box.close()
+    nccl.close()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_mailboxes_two_ranks():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_box, args=(r, 2, 29534, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert not res[0][2] and not res[1][2]
+    if not (res[0][1] and res[1][1]):
+        pytest.skip("CUDA IPC peer mapping is not available on this box: the communicator stayed on NCCL")
+    for rank, _, _, err, got, ref in res:
+        assert err == 0
+        assert ref[:, 1:].sum() == 13 * 4 * 257 * 513              # every pixel of both ranks' images counted, every step
+        for g in got:
+            assert np.array_equal(g, ref)                          # two ranks: a + b in rank order == NCCL's sum, bit for bit
+    assert np.array_equal(res[0][4][0], res[1][4][0])              # and identical on both ranks
