@@ -411,7 +411,7 @@ def run_b200(args, rank, world, local_rank):
         ch = confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak, dist)
         if rank == 0:
             extra["confusion_hist"] = ch
-    if rank == 0 and not args.skip_secondary:
+    if rank == 0 and world == 1 and not args.skip_secondary:        # per-GPU numbers: reported by the N = 1 run only
         kernels += secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit)
         extra["maxsquare"] = maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, aux_ptrs, acc_ptr, go_ptr, n_norm, stream, kit)
         extra["next_rows"] = next_rows(lib, _lib, synth, dev, stream, kit)
