@@ -60,8 +60,9 @@ class ClockSampler:
     BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
     NOTE = {0x4: "sw_power_cap"}
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.interval = interval
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -90,7 +91,7 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._once()
-            time.sleep(0.002)
+            time.sleep(self.interval)
 
     def start(self):
         if self.nv is None:
@@ -282,6 +283,30 @@ def run_b200(args, rank, world, local_rank):
         comm.join(stream)
     torch.cuda.synchronize()
 
+    if os.environ.get("MSQ_BENCH_AB"):      # diagnostic: the timed loop under different clock-sampler settings
+        for tag, interval in (("none", None), ("2ms", 0.002), ("20ms", 0.02), ("none", None), ("2ms", 0.002)):
+            smp = ClockSampler(local_rank, interval) if interval else None
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if smp:
+                smp.start()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(steps):
+                step(i)
+            if comm is not None:
+                comm.join(stream)
+            b.record()
+            torch.cuda.synchronize()
+            if smp:
+                smp.stop()
+            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                sys.stderr.write(f"[ab] sampler {tag}: {float(t.item()) / steps * 1e3:.2f} us/step\n")
+
     # ---- timed region: EXACTLY `steps` steps, barrier + synchronize on both sides, max over ranks
     sampler = ClockSampler(local_rank)
     if world > 1:
@@ -289,6 +314,13 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the last warm-up steps run AFTER the barrier + synchronize, back to back with the timed ones: the first steps after
+    # an idle stream carry the host's launch latency, the sampler thread's start-up and -- on 8 ranks -- tens of
+    # milliseconds of skew between the ranks (measured: 48.8 us/step for the first 2000 steps after the barrier against
+    # 36.7 us/step for every later 2000, MSQ_BENCH_AB=1); they are warm-up, not steady state
+    REWARM = 256
+    for i in range(REWARM):
+        step(steps - REWARM + i)
     ev0.record()
     for i in range(steps):
         step(i)
@@ -443,6 +475,8 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "images_per_gpu": N_IMG, "global_batch": n_norm,
+                           "timing": "CUDA events around exactly `steps` steps on the launching stream, max over ranks; barrier + "
+                                     "synchronize on both sides, the last 256 warm-up steps after the leading barrier",
                            "l2_policy": f"inputs rotate over {POOL} distinct logits buffers "
                                         f"({POOL * lo_bytes / 1e6:.0f} MB > 126 MB L2); outputs likewise",
                            "hot_regime": {"ms_per_step": hot_ms, "value": world * PX_PER_STEP / hot_ms / 1e6,
