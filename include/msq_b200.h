@@ -274,11 +274,13 @@ int msq_comm_join(msq_comm* comm, int lag /* 0 = most recent all-reduce, k = k c
 void msq_comm_destroy(msq_comm* comm);
 
 /* Peer-memory mailboxes (GPUs of one NVLink/NVSwitch box, <= 8 ranks): with them msq_fused_fwd_bwd does not call NCCL at
- * all.  The step's backward kernel PUSHES this rank's [loss | hist] vector into every rank's mailbox with 16-byte
- * {data, flag} stores over NVLink and sums the vectors the peers pushed for the PREVIOUS step, in rank order (bit-identical
- * on every rank): no extra launch, no stream operation between the step's kernels, no host cost.  The all-reduced vector of
- * step i is in that step's out.stats once the backward of step i+1 has run, or after msq_comm_join(comm, 0, stream), which
- * reduces the one pending step; each step in flight therefore needs its own `out` buffer (rotate >= 2).
+ * all.  A second CTA of the step's finalisation kernel PUSHES the [loss | hist] vector this rank produced in the previous
+ * step into every rank's mailbox with 16-byte {data, flag} stores over NVLink, and sums the vectors all ranks pushed for
+ * the step before that, in rank order (bit-identical on every rank): no extra launch, no stream operation between the
+ * step's kernels, no host cost, nothing on the forward -> finalise -> backward critical path.  The all-reduced vector of
+ * step i is in that step's out.stats once step i+2 has been enqueued, or after msq_comm_join(comm, 0, stream), which
+ * completes the two steps still in flight (collective: every rank calls it); each step in flight therefore needs its own
+ * `out` buffer (rotate >= 3).
  * Set-up (collective): every rank calls msq_comm_box_export (allocates its mailbox, returns a 64-byte cudaIpc handle), the
  * caller all-gathers the handles, every rank calls msq_comm_box_open with all of them in rank order.  If either call fails
  * on any rank, do not call box_open: the communicator keeps using ncclAllReduce. */
@@ -288,8 +290,8 @@ int msq_comm_box_active(const msq_comm* comm);                 /* 1: mailboxes i
 int msq_comm_box_errors(msq_comm* comm, unsigned* out);        /* bit 0: a peer's vector never arrived (synchronises) */
 
 /* One library call per training step: msq_fused_fwd + msq_fused_bwd (+ the statistics all-reduce of out.stats when
- * comm != NULL: carried by the backward kernel over the peer-memory mailboxes when they are open (result one step later, see
- * above), else an ncclAllReduce forked after the backward and ordered after the collective issued `lag` steps earlier), for callers
+ * comm != NULL: carried by the finalisation kernel over the peer-memory mailboxes when they are open (result two steps later,
+ * see above), else an ncclAllReduce forked after the backward and ordered after the collective issued `lag` steps earlier), for callers
  * that know the upstream gradient when they call the forward -- lambda_target is a constant
  * (tools/solve_gta5.py:199,217).  grad = *grad_out (device scalar) if grad_out != NULL, else grad_scale. */
 int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,

@@ -266,7 +266,7 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
 // Cells are NCCL-LL style {lo32, flag, hi32, flag}: data and flag travel in the same 8-byte store, so the
 // reader needs no fence: it polls until both flags carry the sequence number it expects.
 constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch box
-constexpr int kBoxSlots = 8;       // ring of sequence numbers; a writer is never more than 5 steps ahead of a reader
+constexpr int kBoxSlots = 8;       // ring of sequence numbers: when vector s is pushed, vectors s-3 .. s-1 may still be read (>= 4 slots)
 constexpr int kBoxCount = 40;      // doubles per vector (1 + 32 classes, rounded up)
 constexpr unsigned kBoxSpinLimit = 1u << 22;     // polls before a cell is declared lost (~ seconds): never hang the GPU
 
