@@ -268,7 +268,7 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
 constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch box
 constexpr int kBoxSlots = 8;       // ring of sequence numbers: when vector s is pushed, vectors s-3 .. s-1 may still be read (>= 4 slots)
 constexpr int kBoxCount = 40;      // doubles per vector (1 + 32 classes, rounded up)
-constexpr unsigned kBoxSpinLimit = 1u << 22;     // polls before a cell is declared lost (~ seconds): never hang the GPU
+constexpr unsigned kBoxSpinLimit = 1u << 24;     // polls (~0.8 us each) before a cell is declared lost: ~13 s, never a hung GPU
 
 // Static part, resident in device memory (written once by msq_comm_box_open).
 struct PeerBoxStatic {
@@ -304,7 +304,9 @@ __device__ __forceinline__ uint4* box_cell(uint4* base, unsigned seq, int src_ra
 __device__ __forceinline__ void box_reduce(const PeerBoxStatic* st, unsigned seq, int count, double* out, int lane) {
     const int world = st->world, rank = st->rank;
     uint4* mine = st->peer[rank];
-    bool lost = false;
+    // the error is sticky: once a peer's vector has been declared lost, no later call waits again (a dead peer costs
+    // ONE time-out, not one per step)
+    bool lost = (*(volatile unsigned*)st->err & 1u) != 0u;
     for (int k = lane; k < count; k += 32) {
         double sum = 0.0;
         for (int p = 0; p < world; ++p) {
