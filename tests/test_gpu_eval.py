@@ -150,7 +150,8 @@ def test_full_size_properties(msq):
 
 # ------------------------------------------------------------------ flip-ensemble evaluation (tools/evaluate.py:120-141)
 @pytest.mark.parametrize("C,shape,scale", [(19, (2, 64, 128), 3.0), (16, (1, 40, 72), 1.0), (13, (1, 33, 65), 5.0),
-                                           (7, (2, 9, 31), 2.0), (19, (1, 512, 1024), 4.0), (19, (1, 17, 3), 0.01)])
+                                           (7, (2, 9, 31), 2.0), (19, (1, 512, 1024), 4.0), (19, (1, 17, 3), 0.01),
+                                           (19, (1, 16, 8), 0.01), (16, (2, 12, 6), 0.02)])
 def test_flip_ensemble_vs_oracle(msq, C, shape, scale):
     from oracle import eval_port
     n, h, w = shape
