@@ -135,3 +135,13 @@ def test_comm_entry_points_reject_bad_arguments(lib):
     assert lib.msq_comm_allreduce_f64(None, None, 1, None) == -1
     assert lib.msq_comm_join(None, 0, None) == -1
     assert lib.msq_error_string(-5).startswith(b"msq:")
+
+
+def test_peer_memory_mailbox_argument_checks(lib):
+    # the mailbox entry points reject null handles before touching CUDA; a NULL communicator has no mailboxes
+    buf = ctypes.create_string_buffer(64)
+    assert lib.msq_comm_box_export(None, buf) == -1
+    assert lib.msq_comm_box_open(None, buf) == -1
+    assert lib.msq_comm_box_active(None) == 0
+    v = ctypes.c_uint(7)
+    assert lib.msq_comm_box_errors(None, ctypes.byref(v)) == -1
