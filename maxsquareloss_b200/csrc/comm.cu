@@ -232,13 +232,15 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
 
 // One call per training step for callers that know the upstream gradient scale when they call the forward
 // (lambda_target is a constant, tools/solve_gta5.py:199,217): msq_fused_fwd + msq_fused_bwd and, when the images are
-// sharded over ranks (comm != NULL), the step's statistics all-reduce -- forked after the backward so that nothing
-// sits between forward -> finalise -> backward, and ordered after the collective issued `lag` steps earlier.  Same
-// kernels and results as the separate calls; it exists to keep the host side of a 35 us step to one library call.
+// sharded over ranks (comm != NULL), the exchange of the step's statistics vector: carried by the finalisation kernel
+// over the peer-memory mailboxes when they are open, else one ncclAllReduce forked after the backward (so that nothing
+// sits between forward -> finalise -> backward) and ordered after the collective issued `lag` steps earlier.  Same
+// kernels and results as the separate calls; it also keeps the host side of a 35 us step to one library call.
+// All steps of one communicator must be enqueued on the same stream (the mailbox protocol relies on stream order).
 extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                                  double ratio, int n_images_norm, void* accum, void* out, void* aux, const float* grad_out,
                                  float grad_scale, float* grad_logits, msq_comm* comm, int lag, msq_stream_t stream) {
-    if (!grad_logits) return MSQ_E_BADARG;
+    if (!grad_logits || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES) return MSQ_E_BADARG;
     if ((((uintptr_t)aux) & 15u) || (((uintptr_t)grad_logits) & 3u)) return MSQ_E_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
     const msq_state_layout lay = msq::make_layout(n, num_class);
