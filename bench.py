@@ -458,10 +458,21 @@ def run_b200(args, rank, world, local_rank):
         traffic, traffic_src = tk["dram_read_bytes"] + tk["dram_write_bytes"], tj["source"]
     except Exception:
         pass
+    issue = None
+    try:        # the bound that does apply: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock)
+        tk = tj["kernels"]["fused_fwd" if "fwd" in dom["kernel"] else "fused_bwd"]
+        peak_ginst = 148 * 4 * (clocks.get("sm_mhz") or 1965) / 1e3
+        issue = {"warp_instructions_per_launch": tk["warp_instructions"], "achieved_Ginst_per_s": tk["warp_instructions"] / dom["ms"] / 1e6,
+                 "peak_Ginst_per_s": peak_ginst, "frac": tk["warp_instructions"] / dom["ms"] / 1e6 / peak_ginst,
+                 "ncu_issue_active_pct": tk["issue_active_pct"], "ncu_pipes_pct": {"xu": tk["xu_pipe_pct"], "fma": tk["fma_pipe_pct"], "alu": tk["alu_pipe_pct"]},
+                 "note": "instruction count from the committed ncu capture; time = this run's CUDA-event time of the launch (incl. the "
+                         "dependent finalisation launch for the forward)"}
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom["achieved_GBps"] / hbm_peak, "traffic": traffic, "kernel": dom["kernel"],
                 "peak_source": peak_src,
-                "traffic_source": traffic_src,
+                "traffic_source": traffic_src, "issue_slots": issue,
                 "note": "the fused kernels move ~18 algorithmic B/pixel each (2.4 B of logits/gradient + the 16 B "
                         "statistics cache) and are FP32-issue/MUFU bound by design (SURVEY.md 8d); the HBM-bound "
                         "kernels of the path are listed under 'kernels'"}
