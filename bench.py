@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
     # an idle stream carry the host's launch latency, the sampler thread's start-up and -- on 8 ranks -- tens of
     # milliseconds of skew between the ranks (measured: 48.8 us/step for the first 2000 steps after the barrier against
     # 36.7 us/step for every later 2000, MSQ_BENCH_AB=1); they are warm-up, not steady state
-    REWARM = 256
+    REWARM = max(256, min(steps, 4000))        # as many again as are timed: whatever the transient is, it is over
     for i in range(REWARM):
         step(steps - REWARM + i)
     ev0.record()
@@ -487,7 +487,7 @@ def run_b200(args, rank, world, local_rank):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "images_per_gpu": N_IMG, "global_batch": n_norm,
                            "timing": "CUDA events around exactly `steps` steps on the launching stream, max over ranks; barrier + "
-                                     "synchronize on both sides, the last 256 warm-up steps after the leading barrier",
+                                     "synchronize on both sides, the last warm-up steps (as many as are timed) after the leading barrier",
                            "l2_policy": f"inputs rotate over {POOL} distinct logits buffers "
                                         f"({POOL * lo_bytes / 1e6:.0f} MB > 126 MB L2); outputs likewise",
                            "hot_regime": {"ms_per_step": hot_ms, "value": world * PX_PER_STEP / hot_ms / 1e6,
