@@ -252,8 +252,8 @@ int  msq_pipe_wait(msq_pipe* pipe, int slot);
 int  msq_pipe_drain(msq_pipe* pipe);
 void msq_pipe_destroy(msq_pipe* pipe);
 
-/* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "conf_ctas" 1|2,
- * "prob_waves" W, "fused_rows" R; 0 = automatic).  Results never depend on them. */
+/* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "conf_ctas" 1|2, "conf_grid" G,
+ * "prob_waves" W, "fused_rows" R, "reserve_sms" S; 0 = automatic).  Results never depend on them. */
 int msq_tune_set(const char* key, int value);
 
 /* ---------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 namespace msq {
 extern int g_conf_agg;      // confusion.cu
 extern int g_conf_ctas_per_sm;
+extern int g_conf_grid;
 extern int g_prob_waves;    // prob_loss.cu
 extern int g_fused_rows;    // fused_loss.cu
 extern int g_reserve_sms;
@@ -61,6 +62,7 @@ extern "C" int msq_state_layout_get(int n_images, int num_class, msq_state_layou
 // Performance-tuning knobs (bench sweeps); results never depend on them.
 //   "conf_agg"   0|1|2  warp aggregation level of the confusion histogram
 //   "conf_ctas"  1|2    1024-thread CTAs per SM of the int64 confusion kernel
+//   "conf_grid"  G      at most G CTAs in the int64 confusion kernel (0 = automatic)
 //   "prob_waves" W      grid of the strict kernels = W x co-resident capacity
 //   "fused_rows" R      about R output rows per CTA in the fused kernels (0 = automatic: one balanced wave)
 //   "reserve_sms" S     the one-wave grids of the fused kernels leave S SMs free (a concurrent NCCL kernel gets them)
@@ -68,6 +70,7 @@ extern "C" int msq_tune_set(const char* key, int value) {
     if (!key) return MSQ_E_BADARG;
     if (!strcmp(key, "conf_agg")) { msq::g_conf_agg = value; return 0; }
     if (!strcmp(key, "conf_ctas")) { msq::g_conf_ctas_per_sm = value; return 0; }
+    if (!strcmp(key, "conf_grid")) { msq::g_conf_grid = value; return 0; }
     if (!strcmp(key, "prob_waves")) { msq::g_prob_waves = value; return 0; }
     if (!strcmp(key, "fused_rows")) { msq::g_fused_rows = value; return 0; }
     if (!strcmp(key, "reserve_sms")) { msq::g_reserve_sms = value; return 0; }

@@ -243,6 +243,9 @@ confusion_logits_kernel(const int64_t* __restrict__ gt, const float* __restrict_
 
 int g_conf_ctas_per_sm = 1;   // tuning knob: 1024-thread CTAs per SM for the int64 kernel (1 or 2)
 int g_conf_agg = 0;   // tuning knob (msq_tune_set), see api.cu; 0 measured fastest on B200
+int g_conf_grid = 0;  // tuning knob: explicit CTA count of the int64 kernel (0 = automatic).  Every CTA ends with up to C*C
+                      // global atomics on the SAME addresses (~10 ns each per address), so for one 8 MB image fewer CTAs
+                      // may beat one per SM; for scripts/ab_conf.py sweeps
 
 template <int AGG>
 static int launch_i64(const int64_t* gt, const int64_t* pred, long long npix, int C, unsigned long long* cm,
@@ -252,6 +255,7 @@ static int launch_i64(const int64_t* gt, const int64_t* pred, long long npix, in
     long long blocks = (groups + kConfBig - 1) / kConfBig;
     const long long cap = (long long)kSMs * (g_conf_ctas_per_sm > 0 ? g_conf_ctas_per_sm : 1);
     if (blocks > cap) blocks = cap;
+    if (g_conf_grid > 0 && blocks > g_conf_grid) blocks = g_conf_grid;
     if (blocks < 1) blocks = 1;
     const size_t smem = (size_t)C * C * sizeof(unsigned) * kConfSub;
     cudaError_t le;
