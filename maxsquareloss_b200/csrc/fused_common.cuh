@@ -8,7 +8,11 @@
 
 namespace msq {
 
-constexpr int kTW = 128;                        // output columns (= threads) per CTA
+#ifndef MSQ_TW
+#define MSQ_TW 128                              // A/B builds: -DMSQ_TW=64 (with MSQ_FWD_MINB / MSQ_BWD_MINB = 8)
+#endif
+constexpr int kTW = MSQ_TW;                     // output columns (= threads) per CTA
+static_assert(kTW % 32 == 0 && kTW >= 32 && kTW <= 256, "kTW: whole warps, at least MSQ_MAX_CLASSES threads");
 constexpr int kRun = 8;                         // backward fast path: output columns per low-res cell and tap side
 #ifndef MSQ_FWD_MINB
 #define MSQ_FWD_MINB 4                          // co-resident CTAs per SM the forward is compiled for

@@ -19,7 +19,10 @@
 namespace msq {
 
 template <int CT, bool PAD>
-__global__ void __launch_bounds__(kTW, 4)
+#ifndef MSQ_SRC_MINB
+#define MSQ_SRC_MINB 4
+#endif
+__global__ void __launch_bounds__(kTW, MSQ_SRC_MINB)
 source_ce_fwd_kernel(const float* __restrict__ lo, const int64_t* __restrict__ label, FusedGeo g, int n_img, unsigned units,
                      State st, void* __restrict__ aux, float* __restrict__ zero_buf, unsigned zero_count,
                      unsigned long long* __restrict__ cm) {
