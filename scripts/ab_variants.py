@@ -1,0 +1,41 @@
+"""A/B of build variants of the fused kernels (development aid for the next round).
+
+    python scripts/ab_variants.py build      # here, on the CPU: nvcc cross-compiles every variant into lib/variants/
+    python scripts/ab_variants.py run        # on the B200 (gpurun): correctness spot check + fwd / bwd / step times per variant
+    python scripts/ab_variants.py test NAME  # on the B200: the fused parity tests against one variant
+
+The built libraries are git-ignored but travel to the GPU box with the working tree."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VARDIR = os.path.join(ROOT, "maxsquareloss_b200", "lib", "variants")
+VARIANTS = {
+    "base": (),
+    "tw64": ("MSQ_TW=64", "MSQ_FWD_MINB=8", "MSQ_BWD_MINB=8", "MSQ_MULTI_MINB=4", "MSQ_SRC_MINB=8"),
+    "ring2": ("MSQ_BWD_CACHE_RING=2",),
+    "ring4": ("MSQ_BWD_CACHE_RING=4",),
+    "tw64_ring4": ("MSQ_TW=64", "MSQ_FWD_MINB=8", "MSQ_BWD_MINB=8", "MSQ_MULTI_MINB=4", "MSQ_SRC_MINB=8", "MSQ_BWD_CACHE_RING=4"),
+}
+
+
+def path(name):
+    return os.path.join(VARDIR, f"libmsq_{name}.so")
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "run"
+    if cmd == "build":
+        from maxsquareloss_b200 import build
+        os.makedirs(VARDIR, exist_ok=True)
+        for name, defs in VARIANTS.items():
+            print(name, build.build(force=True, defines=defs + ("MSQ_VARIANT=1",), out=path(name)), flush=True)
+    elif cmd == "run":
+        for name in VARIANTS:
+            if not os.path.exists(path(name)):
+                print(f"{name}: not built"); continue
+            env = dict(os.environ, MSQ_B200_LIB=path(name))
+            subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ab_fused.py")], env=env)
+    elif cmd == "test":
+        env = dict(os.environ, MSQ_B200_LIB=path(sys.argv[2]))
+        sys.exit(subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-x", "-q", "-k",
+                                 "fused or multi or source or entropy or step"], env=env).returncode)
