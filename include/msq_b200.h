@@ -282,10 +282,12 @@ void msq_comm_destroy(msq_comm* comm);
  * completes the two steps still in flight (collective: every rank calls it); each step in flight therefore needs its own
  * `out` buffer (rotate >= 3).
  * Set-up (collective): every rank calls msq_comm_box_export (allocates its mailbox, returns a 64-byte cudaIpc handle), the
- * caller all-gathers the handles, every rank calls msq_comm_box_open with all of them in rank order.  If either call fails
- * on any rank, do not call box_open: the communicator keeps using ncclAllReduce. */
+ * caller all-gathers the handles, every rank calls msq_comm_box_open with all of them in rank order (maps the peers), the
+ * ranks agree on whether ALL of them succeeded, and every rank calls msq_comm_box_enable(comm, 1) -- or none does, and the
+ * communicator keeps using ncclAllReduce (CUDA IPC not permitted, no peer access, more than 8 ranks). */
 int msq_comm_box_export(msq_comm* comm, void* handle64 /* host, 64 bytes out */);
 int msq_comm_box_open(msq_comm* comm, const void* handles /* host, world x 64 bytes, rank order */);
+int msq_comm_box_enable(msq_comm* comm, int on);               /* on: needs a successful box_open; no steps in flight */
 int msq_comm_box_active(const msq_comm* comm);                 /* 1: mailboxes in use, 0: NCCL */
 int msq_comm_box_errors(msq_comm* comm, unsigned* out);        /* bit 0: a peer's vector never arrived (synchronises) */
 

@@ -18,7 +18,7 @@ MODE_IW = 1
 SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
            "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
            "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_join", "msq_comm_destroy",
-           "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_active", "msq_comm_box_errors",
+           "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_enable", "msq_comm_box_active", "msq_comm_box_errors",
            "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
@@ -105,6 +105,8 @@ def load():
         lib.msq_comm_box_export.argtypes = [vp, vp]
         lib.msq_comm_box_open.restype = i32
         lib.msq_comm_box_open.argtypes = [vp, vp]
+        lib.msq_comm_box_enable.restype = i32
+        lib.msq_comm_box_enable.argtypes = [vp, i32]
         lib.msq_comm_box_active.restype = i32
         lib.msq_comm_box_active.argtypes = [vp]
         lib.msq_comm_box_errors.restype = i32

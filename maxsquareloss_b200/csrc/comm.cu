@@ -64,7 +64,7 @@ struct msq_comm {
     uint4* box_peer[msq::kMaxPeers];      // every rank's mailbox as mapped here (box_peer[rank] == box_local)
     unsigned* box_err;                    // device error word
     msq::PeerBoxStatic* box_static;       // device copy of {world, rank, err, peers}
-    bool box_ready;
+    bool box_mapped, box_ready;           // peers mapped / mailbox path switched on (msq_comm_box_enable)
     unsigned box_seq;                     // steps issued so far = sequence number of the newest vector
     double* box_last;                     // statistics of step box_seq: produced, not pushed yet (NULL: none pending)
     double* box_pushed;                   // statistics of step box_seq-1: pushed, not reduced yet (NULL: none pending)
@@ -101,7 +101,7 @@ extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm*
     msq_comm* c = new (std::nothrow) msq_comm();
     if (!c) return (int)cudaErrorMemoryAllocation;
     c->world = world; c->rank = rank; c->issued = 0;
-    c->box_local = nullptr; c->box_err = nullptr; c->box_static = nullptr; c->box_ready = false; c->box_seq = 0u; c->box_last = nullptr; c->box_pushed = nullptr; c->box_last_count = 0; c->box_pushed_count = 0;
+    c->box_local = nullptr; c->box_err = nullptr; c->box_static = nullptr; c->box_mapped = false; c->box_ready = false; c->box_seq = 0u; c->box_last = nullptr; c->box_pushed = nullptr; c->box_last_count = 0; c->box_pushed_count = 0;
     for (int p = 0; p < msq::kMaxPeers; ++p) c->box_peer[p] = nullptr;
     nccl_unique_id id;
     memcpy(&id, id128, sizeof(id));
@@ -199,7 +199,17 @@ extern "C" int msq_comm_box_open(msq_comm* c, const void* handles /* world x 64 
     cudaError_t e = cudaMemcpy(c->box_static, &st, sizeof(st), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
-    c->box_ready = true;
+    c->box_mapped = true;
+    return 0;
+}
+
+// Switch the mailbox path on (only if every peer is mapped) or off.  The caller enables it on all ranks or on none:
+// after msq_comm_box_open it agrees on the outcome across the ranks (an all-reduce(min) of "my open succeeded").
+extern "C" int msq_comm_box_enable(msq_comm* c, int on) {
+    if (!c) return MSQ_E_BADARG;
+    if (on && !c->box_mapped) return MSQ_E_BADARG;
+    if (c->box_last) return MSQ_E_BADARG;          // steps in flight: msq_comm_join first
+    c->box_ready = on != 0;
     return 0;
 }
 

@@ -115,13 +115,13 @@ class StatsComm:
         dist.all_gather(allh, t, group=group)
         allh = torch.stack(allh).cpu()
         if not bool((allh[:, 64] == 1).all()):
-            return
+            return                                       # every rank sees the same table: all of them return here
         blob = bytes(allh[:, :64].contiguous().numpy().tobytes())
         rc = self._lib.msq_comm_box_open(self._h, blob)
         flag = torch.tensor([1 if rc == 0 else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if int(flag.item()) != 1:
-            raise RuntimeError("libmsq_b200: peer-memory mailboxes opened on some ranks only; set MSQ_PEERBOX=0")
+        if int(flag.item()) == 1:                        # all ranks mapped all peers: switch the path on everywhere
+            self._libmod.check(self._lib.msq_comm_box_enable(self._h, 1))
         self.peer_memory = bool(self._lib.msq_comm_box_active(self._h))
 
     def errors(self):

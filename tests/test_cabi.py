@@ -143,5 +143,6 @@ def test_peer_memory_mailbox_argument_checks(lib):
     assert lib.msq_comm_box_export(None, buf) == -1
     assert lib.msq_comm_box_open(None, buf) == -1
     assert lib.msq_comm_box_active(None) == 0
+    assert lib.msq_comm_box_enable(None, 1) == -1
     v = ctypes.c_uint(7)
     assert lib.msq_comm_box_errors(None, ctypes.byref(v)) == -1
