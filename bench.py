@@ -558,16 +558,16 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
         ev._pending = True
         return ms, ev.Mean_Intersection_over_Union(), int(ev.confusion_matrix.sum())
 
-    def per_image():
-        for k in range(len(mine)):
-            j = k % pool
+    def per_image():                                         # validation image i is pool entry i % pool on EVERY sharding:
+        for i in mine:                                       # the accumulated matrix (and mIoU) does not depend on the rank count
+            j = i % pool
             rc = lib.msq_confusion_i64(gp[j], pp[j], px_img, Cv, cm_ptr, cm_ptr + 8 * Cv * Cv, stream)
             if rc:
                 _lib.check(rc)
 
     def api_per_image():
-        for k in range(len(mine)):
-            ev.add_batch(gts[k % pool], prs[k % pool])
+        for i in mine:
+            ev.add_batch(gts[i % pool], prs[i % pool])
 
     B = 16
     stacks = [(torch.cat(gts[k:k + B]).contiguous(), torch.cat(prs[k:k + B]).contiguous()) for k in (0, B)]
@@ -588,8 +588,8 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
     lgp = [t.data_ptr() for t in lgs]
 
     def logits():
-        for k in range(len(mine)):
-            rc = lib.msq_confusion_logits_f32(gp[k % pool], lgp[k % lg_pool], 1, Cv, px_img, cm_ptr, stream)
+        for i in mine:
+            rc = lib.msq_confusion_logits_f32(gp[i % pool], lgp[i % lg_pool], 1, Cv, px_img, cm_ptr, stream)
             if rc:
                 _lib.check(rc)
 
