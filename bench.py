@@ -528,12 +528,15 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
       per_image  one Eval.add_batch / msq_confusion_i64 launch per image, as tools/train_source.py:429-492 calls it
       batched    the rank's images in launches of 16 (a caller that stacks its validation batch)
       logits     per image from fp32 logits (1,16,512,1024): the callers' np.argmax fused into the kernel"""
-    Cv, HWv, n_total, pool = 16, (512, 1024), 500, 32
+    Cv, HWv, n_total, pool = 16, (512, 1024), 500, 128
     mine = list(range(rank, n_total, world))
     px_img = HWv[0] * HWv[1]
-    gts = [synth.blocky_labels(1, HWv, Cv, 1000 + i).to(dev) for i in range(pool)]
-    prs = [synth.noisy_prediction(gts[i].cpu(), Cv, 1000 + i).to(dev) for i in range(pool)]     # 32 x 8.4 MB = 268 MB > L2
-    gp, pp = [t.data_ptr() for t in gts], [t.data_ptr() for t in prs]
+    # validation image i is pool entry i % pool on EVERY sharding, so the accumulated matrix (and mIoU) does not depend on the
+    # rank count; a rank touches >= 16 distinct entries (>= 134 MB > L2) at up to 8 ranks and generates only those
+    entries = sorted({i % pool for i in mine})
+    gts = {e: synth.blocky_labels(1, HWv, Cv, 1000 + e).to(dev) for e in entries}
+    prs = {e: synth.noisy_prediction(gts[e].cpu(), Cv, 1000 + e).to(dev) for e in entries}
+    gp, pp = {e: t.data_ptr() for e, t in gts.items()}, {e: t.data_ptr() for e, t in prs.items()}
     ev = msq.Eval(Cv, device=dev)
     cm_ptr = ev._dev.data_ptr()
 
@@ -558,8 +561,8 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
         ev._pending = True
         return ms, ev.Mean_Intersection_over_Union(), int(ev.confusion_matrix.sum())
 
-    def per_image():                                         # validation image i is pool entry i % pool on EVERY sharding:
-        for i in mine:                                       # the accumulated matrix (and mIoU) does not depend on the rank count
+    def per_image():
+        for i in mine:
             j = i % pool
             rc = lib.msq_confusion_i64(gp[j], pp[j], px_img, Cv, cm_ptr, cm_ptr + 8 * Cv * Cv, stream)
             if rc:
@@ -570,7 +573,8 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
             ev.add_batch(gts[i % pool], prs[i % pool])
 
     B = 16
-    stacks = [(torch.cat(gts[k:k + B]).contiguous(), torch.cat(prs[k:k + B]).contiguous()) for k in (0, B)]
+    groups = [entries[:B], entries[B:2 * B] if len(entries) >= 2 * B else entries[:B]]
+    stacks = [(torch.cat([gts[e] for e in grp]).contiguous(), torch.cat([prs[e] for e in grp]).contiguous()) for grp in groups]
 
     def batched():
         left, k = len(mine), 0
@@ -588,8 +592,8 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
     lgp = [t.data_ptr() for t in lgs]
 
     def logits():
-        for i in mine:
-            rc = lib.msq_confusion_logits_f32(gp[i % pool], lgp[i % lg_pool], 1, Cv, px_img, cm_ptr, stream)
+        for k, i in enumerate(mine):
+            rc = lib.msq_confusion_logits_f32(gp[i % pool], lgp[k % lg_pool], 1, Cv, px_img, cm_ptr, stream)
             if rc:
                 _lib.check(rc)
 
