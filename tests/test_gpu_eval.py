@@ -187,3 +187,24 @@ def test_flip_ensemble_identical_views_reduce_to_plain_argmax(msq):
         ev.add_batch_flip(gt.cuda(), a.cuda(), a[:, :, :16].cuda())
     with pytest.raises(RuntimeError):
         ev.add_batch_flip(gt, a, a)
+
+
+def test_flip_ensemble_golden_from_reference_validate(msq):
+    """Vectors frozen from the reference's own Evaluater.validate with --flip (oracle/make_golden_flip.py): logits for the
+    image and for its mirror image as the model returned them, float labels; confusion matrix and mIoU bit-exact.  No pixel
+    of these cases has its two best averaged probabilities within 2e-4 relative."""
+    import json
+    import os
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(GOLDEN, "flip_kats.json")) as f:
+        cases = json.load(f)["cases"]
+    t = np.load(os.path.join(GOLDEN, "flip_tensors.npz"))
+    for case in cases:
+        name, C = case["name"], case["C"]
+        ev = msq.Eval(C)
+        for b in range(case["batches"]):
+            ev.add_batch_flip(torch.from_numpy(t[f"{name}/label{b}"].astype(np.int64)).cuda(),
+                              torch.from_numpy(t[f"{name}/pred{b}"]).cuda(), torch.from_numpy(t[f"{name}/pred_flip{b}"]).cuda())
+        assert np.array_equal(ev.confusion_matrix, t[f"{name}/cm"]), name
+        miou = ev.Mean_Intersection_over_Union()
+        assert (list(miou) if isinstance(miou, tuple) else miou) == case["miou"], name
