@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSQ_ABI_VERSION 4
+#define MSQ_ABI_VERSION 5
 #define MSQ_MAX_CLASSES 32          /* reference uses 13 / 16 / 19 */
 
 #define MSQ_E_BADARG   (-1)         /* null pointer, non-positive size, C > MSQ_MAX_CLASSES */
@@ -38,6 +38,8 @@ extern "C" {
 #define MSQ_E_SMEM     (-3)         /* tile does not fit shared memory */
 #define MSQ_E_NCCL     (-5)         /* libnccl.so.2 could not be loaded, or an NCCL call failed */
 #define MSQ_E_ALIGN    (-4)         /* pointer not aligned for its element type */
+#define MSQ_E_PEER     (-6)         /* a peer's statistics vector did not arrive within the mailbox time-out */
+#define MSQ_E_NOTREADY (-7)         /* msq_comm_result: that step's all-reduced vector has not been produced yet */
 
 #define MSQ_MODE_MAXSQUARE 0        /* utils/loss.py:104-119  MaxSquareloss      */
 #define MSQ_MODE_IW        1        /* utils/loss.py:69-102   IW_MaxSquareloss   */
@@ -170,6 +172,19 @@ int msq_entropy_bwd(int mode, const float* logits, int n, int num_class, int h, 
                     int n_images_norm, const void* out, const void* aux, const float* grad_out, float* grad_logits,
                     int grad_is_zeroed, msq_stream_t stream);
 
+/* Strict MinEnt: the reference classes on full-resolution tensors and an ARBITRARY target (utils/loss.py:23-35, 46-67):
+ *   mode MSQ_MODE_MAXSQUARE  softCrossEntropy:    mean( (-log_softmax(inputs,1) * target)[target != ignore_index] )
+ *   mode MSQ_MODE_IW         IWsoftCrossEntropy:  sum( (-log_softmax * target * w[argmax_c inputs])[mask] ) / (N C)
+ *   inputs, target  float32 [N,C,H*W]
+ * Buffers as msq_prob_fwd (out.hist_out = per-image histogram of argmax(inputs), out.weights, out.loss, out.stats).
+ * The backward writes d/d inputs and, when grad_target != NULL, d/d target (the trainers' target = softmax(inputs) is
+ * attached to the graph, tools/solve_gta5.py:188-190): both overwritten, zeros where target == ignore_index. */
+int msq_softce_fwd(int mode, const float* inputs, const float* target, int n, int num_class, int64_t hw,
+                   double ratio, int ignore_index, int n_images_norm, void* accum, void* out, msq_stream_t stream);
+int msq_softce_bwd(int mode, const float* inputs, const float* target, int n, int num_class, int64_t hw,
+                   int ignore_index, int n_images_norm, const void* out, const float* grad_out,
+                   float* grad_inputs, float* grad_target /* nullable */, msq_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Multi-level self-produced guidance ("MaxSquare+IW+Multi", BASELINE config 3): the inline
  * trainer code tools/solve_gta5.py:183,192,206-215 == tools/solve_crosscity.py:235-243,
@@ -226,6 +241,24 @@ int msq_confusion_i64(const int64_t* gt, const int64_t* pred, int64_t npix, int 
 int msq_confusion_logits_f32(const int64_t* gt, const float* logits, int n, int num_class,
                              int64_t hw, unsigned long long* cm, msq_stream_t stream);
 
+/* K (gt, pred) pairs in ONE launch: the reference's evaluation loops call Eval.add_batch once per image
+ * (tools/train_source.py:429-492, tools/evaluate.py:99-202, tools/analysis.py:200-229), and one 8 MB launch per image is
+ * launch-bound.  gt / pred / npix are HOST arrays of k device pointers / pixel counts (they travel as kernel parameters,
+ * 32 pairs per launch).
+ *   cm_stride = 0          every pair is ACCUMULATED into cm[C*C]   (k deferred add_batch calls)
+ *   cm_stride >= C*C       pair j is ACCUMULATED into cm + j*cm_stride: one matrix per image, what tools/analysis.py:200-229
+ *                          obtains with add_batch / metrics / reset() per image (no empty pairs in this mode)
+ *   total (nullable)       every pair is additionally accumulated here (analysis.py's totalEval) */
+int msq_confusion_i64_multi(const int64_t* const* gt, const int64_t* const* pred, const int64_t* npix, int k,
+                            int num_class, unsigned long long* cm, int64_t cm_stride, unsigned long long* total,
+                            unsigned int* errs, msq_stream_t stream);
+
+/* Per-image matrices from a batch of fp32 logits [N,C,H*W] (argmax fused): image i is ACCUMULATED into
+ * cm_per_image + i*C*C, and every image into total when it is not NULL. */
+int msq_confusion_per_image_logits_f32(const int64_t* gt, const float* logits, int n, int num_class, int64_t hw,
+                                       unsigned long long* cm_per_image, unsigned long long* total /* nullable */,
+                                       msq_stream_t stream);
+
 /* Flip-ensemble evaluation (tools/evaluate.py:120-141, --flip), fused: argmax_c of
  * (softmax(logits)[..., x] + softmax(logits_flipped)[..., W-1-x]) / 2 against gt, ACCUMULATED into cm.
  * logits_flipped is the model's output for the horizontally flipped image, NOT flipped back. */
@@ -277,25 +310,41 @@ void msq_comm_destroy(msq_comm* comm);
  * all.  A second CTA of the step's finalisation kernel PUSHES the [loss | hist] vector this rank produced in the previous
  * step into every rank's mailbox with 16-byte {data, flag} stores over NVLink, and sums the vectors all ranks pushed for
  * the step before that, in rank order (bit-identical on every rank): no extra launch, no stream operation between the
- * step's kernels, no host cost, nothing on the forward -> finalise -> backward critical path.  The all-reduced vector of
- * step i is in that step's out.stats once step i+2 has been enqueued, or after msq_comm_join(comm, 0, stream), which
- * completes the two steps still in flight (collective: every rank calls it); each step in flight therefore needs its own
- * `out` buffer (rotate >= 3).
+ * step's kernels, no host cost, nothing on the forward -> finalise -> backward critical path.
+ * Ownership: the step's own vector and the all-reduced vectors live in device rings the COMMUNICATOR allocates (8 steps
+ * deep); the caller's `out` keeps the rank-LOCAL statistics and is never read or written after the call that was given it
+ * (it may be reused or freed at once, in stream order).  The all-reduced vector of step i is fetched with msq_comm_result
+ * once step i+2 has been enqueued, or after msq_comm_join(comm, 0, stream), which completes the steps still in flight
+ * (collective: every rank calls it).
  * Set-up (collective): every rank calls msq_comm_box_export (allocates its mailbox, returns a 64-byte cudaIpc handle), the
  * caller all-gathers the handles, every rank calls msq_comm_box_open with all of them in rank order (maps the peers), the
  * ranks agree on whether ALL of them succeeded, and every rank calls msq_comm_box_enable(comm, 1) -- or none does, and the
- * communicator keeps using ncclAllReduce (CUDA IPC not permitted, no peer access, more than 8 ranks). */
+ * communicator keeps using ncclAllReduce (CUDA IPC not permitted, no peer access, more than 8 ranks).
+ * Liveness: a reduction waits for a peer's vector for msq_comm_box_timeout seconds (default 600, or MSQ_BOX_TIMEOUT_S);
+ * after that the vector of THAT step becomes NaN, the error is returned as MSQ_E_PEER by the next msq_fused_fwd_bwd /
+ * msq_comm_join (once per loss), and the next step waits afresh: a slow rank costs the statistics it missed, nothing else. */
 int msq_comm_box_export(msq_comm* comm, void* handle64 /* host, 64 bytes out */);
 int msq_comm_box_open(msq_comm* comm, const void* handles /* host, world x 64 bytes, rank order */);
 int msq_comm_box_enable(msq_comm* comm, int on);               /* on: needs a successful box_open; no steps in flight */
 int msq_comm_box_active(const msq_comm* comm);                 /* 1: mailboxes in use, 0: NCCL */
-int msq_comm_box_errors(msq_comm* comm, unsigned* out);        /* bit 0: a peer's vector never arrived (synchronises) */
+int msq_comm_box_errors(msq_comm* comm, unsigned* out);        /* bit 0: a peer's vector did not arrive in time (synchronises) */
+int msq_comm_box_timeout(msq_comm* comm, double seconds);      /* per-vector wait limit (synchronises the device) */
 
-/* One library call per training step: msq_fused_fwd + msq_fused_bwd (+ the statistics all-reduce of out.stats when
+/* All-reduced [loss | class hist] of the msq_fused_fwd_bwd step issued `lag` steps before the most recent one (0 = the most
+ * recent), copied device-to-device into dst (count <= 1 + C doubles) on `stream`.  MSQ_E_NOTREADY if that vector has not
+ * been produced yet (mailboxes: two steps later or after msq_comm_join; at most 6 steps back). */
+int msq_comm_result(msq_comm* comm, int lag, double* dst, int count, msq_stream_t stream);
+
+/* One library call per training step: msq_fused_fwd + msq_fused_bwd (+ the all-reduce of the step's statistics vector when
  * comm != NULL: carried by the finalisation kernel over the peer-memory mailboxes when they are open (result two steps later,
- * see above), else an ncclAllReduce forked after the backward and ordered after the collective issued `lag` steps earlier), for callers
- * that know the upstream gradient when they call the forward -- lambda_target is a constant
- * (tools/solve_gta5.py:199,217).  grad = *grad_out (device scalar) if grad_out != NULL, else grad_scale. */
+ * see above), else an ncclAllReduce of the communicator's copy forked after the backward and ordered after the collective issued
+ * `lag` steps earlier), for callers that know the upstream gradient when they call the forward -- lambda_target is a constant
+ * (tools/solve_gta5.py:199,217).  grad = *grad_out (device scalar) if grad_out != NULL, else grad_scale.
+ * out.stats holds the rank-LOCAL vector; fetch the all-reduced one with msq_comm_result.
+ * Ordering contract of every fused kernel chain in this library: the kernels are launched with programmatic stream
+ * serialisation and stage their logits tile BEFORE waiting for the preceding kernel, so `logits` must be complete when the
+ * step's first kernel is launched; a producer that itself triggers dependents early (griddepcontrol.launch_dependents
+ * before its last store) must not directly precede them in the stream. */
 int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                       double ratio, int n_images_norm, void* accum, void* out, void* aux /* nullable */,
                       const float* grad_out /* nullable */, float grad_scale, float* grad_logits,

@@ -16,9 +16,9 @@ MODE_IW = 1
 
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
-           "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
+           "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_i64_multi", "msq_confusion_per_image_logits_f32", "msq_softce_fwd", "msq_softce_bwd", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
            "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_join", "msq_comm_destroy",
-           "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_enable", "msq_comm_box_active", "msq_comm_box_errors",
+           "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_enable", "msq_comm_box_active", "msq_comm_box_errors", "msq_comm_box_timeout", "msq_comm_result",
            "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
@@ -79,6 +79,14 @@ def load():
         lib.msq_confusion_flip_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
         lib.msq_confusion_i64.restype = i32
         lib.msq_confusion_i64.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+        lib.msq_confusion_i64_multi.restype = i32
+        lib.msq_confusion_i64_multi.argtypes = [vp, vp, vp, i32, i32, vp, i64, vp, vp, vp]
+        lib.msq_confusion_per_image_logits_f32.restype = i32
+        lib.msq_confusion_per_image_logits_f32.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp]
+        lib.msq_softce_fwd.restype = i32
+        lib.msq_softce_fwd.argtypes = [i32, vp, vp, i32, i32, i64, dbl, i32, i32, vp, vp, vp]
+        lib.msq_softce_bwd.restype = i32
+        lib.msq_softce_bwd.argtypes = [i32, vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp]
         lib.msq_confusion_logits_f32.restype = i32
         lib.msq_confusion_logits_f32.argtypes = [vp, vp, i32, i32, i64, vp, vp]
         lib.msq_tune_set.restype = i32
@@ -111,11 +119,15 @@ def load():
         lib.msq_comm_box_active.argtypes = [vp]
         lib.msq_comm_box_errors.restype = i32
         lib.msq_comm_box_errors.argtypes = [vp, c.POINTER(c.c_uint)]
+        lib.msq_comm_box_timeout.restype = i32
+        lib.msq_comm_box_timeout.argtypes = [vp, dbl]
+        lib.msq_comm_result.restype = i32
+        lib.msq_comm_result.argtypes = [vp, i32, vp, i32, vp]
         lib.msq_comm_destroy.restype = None
         lib.msq_comm_destroy.argtypes = [vp]
         lib.msq_pipe_destroy.restype = None
         lib.msq_pipe_destroy.argtypes = [vp]
-        if lib.msq_abi_version() != 4:
+        if lib.msq_abi_version() != 5:
             raise RuntimeError("libmsq_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmsq_b200.so")
-SOURCES = ["api.cu", "confusion.cu", "eval_flip.cu", "prob_loss.cu", "fused_loss.cu", "guidance.cu", "source_ce.cu", "host_pipe.cu", "comm.cu"]
+SOURCES = ["api.cu", "confusion.cu", "eval_flip.cu", "prob_loss.cu", "softce.cu", "fused_loss.cu", "guidance.cu", "source_ce.cu", "host_pipe.cu", "comm.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "fused_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "msq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC",

@@ -20,17 +20,21 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
     pdl_trigger();          // the backward may start its prologue now
     pdl_wait();             // ... but this kernel needs every forward CTA's atomics
     if (blockIdx.x == 1) {  // sharded step: the statistics exchange over NVLink peer memory rides along (PeerBox, common.cuh)
-        if (threadIdx.x < 32) box_exchange(box.st, box.cur, box.prev_out, box.seq, box.count, box.prev_count, (int)threadIdx.x);
+        if (threadIdx.x < 32) box_exchange(box, (int)threadIdx.x);
         return;
     }
     finalize_body(st, mode, n, C, r32, omr32, n_norm, kept_dense, multi, loss_kind);
+    if (box.keep) {         // this step's own [loss | hist] into the communicator's ring: pushed by the NEXT step's exchange
+        __syncthreads();
+        for (int k = threadIdx.x; k < box.keep_count; k += blockDim.x) box.keep[k] = st.stats[k];
+    }
 }
 
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                     unsigned long long kept_dense, cudaStream_t stream, int multi, int loss_kind, const PeerBox* box) {
     const int warps = n < 8 ? n : 8;
     const PeerBox bx = box ? *box : PeerBox{};
-    const cudaError_t e = launch_pdl(finalize_kernel, dim3(bx.st ? 2 : 1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
+    const cudaError_t e = launch_pdl(finalize_kernel, dim3((bx.st && (bx.cur || bx.prev_out)) ? 2 : 1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
                                      n_norm, kept_dense, multi, loss_kind, bx);
     if (e != cudaSuccess) return (int)e;
     MSQ_CHECK_LAUNCH();
@@ -49,6 +53,8 @@ extern "C" const char* msq_error_string(int code) {
         case MSQ_E_SMEM: return "msq: low-resolution tile does not fit in shared memory";
         case MSQ_E_ALIGN: return "msq: pointer is not aligned for its element type";
         case MSQ_E_NCCL: return "msq: libnccl.so.2 could not be loaded, or an NCCL call failed";
+        case MSQ_E_PEER: return "msq: a peer's statistics vector did not arrive within the mailbox time-out (that step's all-reduced statistics are NaN)";
+        case MSQ_E_NOTREADY: return "msq: that step's all-reduced statistics do not exist yet (two steps later, or after msq_comm_join)";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "msq: unknown error";
     }
 }

@@ -10,6 +10,8 @@
 // when the statistics are consumed.  libnccl.so.2 is resolved at run time (dlopen: PyTorch has it
 // loaded already), so the library has no link-time NCCL dependency.
 #include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
 #include <new>
 #include "common.cuh"
 
@@ -59,33 +61,54 @@ struct msq_comm {
     cudaEvent_t fork, done[kRing];        // done[n % kRing]: completion of the n-th all-reduce
     int world, rank;
     unsigned long long issued;
-    // peer-memory mailboxes (see PeerBox, common.cuh): used by msq_fused_fwd_bwd instead of ncclAllReduce
+    // ---- per-step statistics of msq_fused_fwd_bwd.  Step k (1, 2, ...) owns slot k % kBoxSlots of two device rings the
+    //      COMMUNICATOR allocates: no pointer into a caller's buffer is kept across calls (round-1 advice) ----
+    double* ring;                         // cudaMalloc: [2][kBoxSlots][kBoxCount]
+    double* box_vec;                      // ring + 0: this rank's vector of step k (written by that step's finalisation kernel)
+    double* box_red;                      // ring + 1: the all-reduced vector of step k
+    int count[msq::kBoxSlots];            // doubles in the vector of the step that owns the slot
+    unsigned long long ar_index[msq::kBoxSlots];      // NCCL path: which all-reduce (c->issued numbering) carries the slot
+    unsigned seq;                         // steps issued
+    unsigned pushed, reduced;             // mailbox path: highest step whose push / reduction has been enqueued
+    // ---- peer-memory mailboxes (see PeerBox, common.cuh) ----
     uint4* box_local;                     // this rank's mailbox (cudaMalloc)
     uint4* box_peer[msq::kMaxPeers];      // every rank's mailbox as mapped here (box_peer[rank] == box_local)
-    unsigned* box_err;                    // device error word
-    msq::PeerBoxStatic* box_static;       // device copy of {world, rank, err, peers}
+    unsigned* err_host;                   // cudaHostAlloc(mapped): [0] bits, [1] vectors lost so far
+    unsigned err_reported;                // losses already returned to the caller as MSQ_E_PEER
+    msq::PeerBoxStatic* box_static;       // device copy of {world, rank, err, timeout, peers}
+    msq::PeerBoxStatic box_static_host;
     bool box_mapped, box_ready;           // peers mapped / mailbox path switched on (msq_comm_box_enable)
-    unsigned box_seq;                     // steps issued so far = sequence number of the newest vector
-    double* box_last;                     // statistics of step box_seq: produced, not pushed yet (NULL: none pending)
-    double* box_pushed;                   // statistics of step box_seq-1: pushed, not reduced yet (NULL: none pending)
-    int box_last_count, box_pushed_count;
 };
 
 namespace {
 constexpr size_t kBoxBytes = sizeof(uint4) * msq::kBoxSlots * msq::kMaxPeers * msq::kBoxCount;
+constexpr size_t kRingDoubles = (size_t)msq::kBoxSlots * msq::kBoxCount;
 
-// completes the two steps still in flight (the steps themselves carry the exchange in their finalisation kernels):
-// pushes the newest vector, reduces the one before it, then reduces the newest in place
-__global__ void __launch_bounds__(32) box_flush_kernel(const msq::PeerBox box, double* last) {
-    msq::box_exchange(box.st, box.cur, box.prev_out, box.seq, box.count, box.prev_count, (int)threadIdx.x);
+// completes the steps still in flight (the steps themselves carry the exchange in their finalisation kernels):
+// pushes the newest vector and reduces the one before it (box), then reduces the newest (last_seq -> last_out)
+__global__ void __launch_bounds__(32) box_flush_kernel(const msq::PeerBox box, unsigned last_seq, int last_count, double* last_out) {
+    msq::box_exchange(box, (int)threadIdx.x);
     __syncwarp();
-    msq::box_reduce(box.st, box.seq, box.count, last, (int)threadIdx.x);
+    if (last_out) msq::box_reduce(box.st, last_seq, last_count, last_out, (int)threadIdx.x);
 }
 
-msq::PeerBox make_box(const msq_comm* c) {
-    msq::PeerBox b = {};
-    b.st = c->box_static;
-    return b;
+inline double* vec_slot(const msq_comm* c, unsigned seq) { return c->box_vec + (size_t)(seq % msq::kBoxSlots) * msq::kBoxCount; }
+inline double* red_slot(const msq_comm* c, unsigned seq) { return c->box_red + (size_t)(seq % msq::kBoxSlots) * msq::kBoxCount; }
+
+// a peer's vector was lost since the last call: reported ONCE per loss (stale by at most the steps in flight: the words
+// live in mapped host memory and are read without synchronising)
+int peer_error(msq_comm* c) {
+    if (!c->err_host) return 0;
+    const unsigned lost = ((volatile unsigned*)c->err_host)[1];
+    if (lost != c->err_reported) { c->err_reported = lost; return MSQ_E_PEER; }
+    return 0;
+}
+
+unsigned long long default_timeout_ns() {
+    const char* e = getenv("MSQ_BOX_TIMEOUT_S");
+    double sec = e ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    return (unsigned long long)(sec * 1e9);
 }
 }  // namespace
 
@@ -98,21 +121,24 @@ extern "C" int msq_comm_unique_id(void* id128) {
 extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm** out) {
     if (!id128 || !out || world < 1 || rank < 0 || rank >= world) return MSQ_E_BADARG;
     if (!nccl().ok) return MSQ_E_NCCL;
-    msq_comm* c = new (std::nothrow) msq_comm();
+    msq_comm* c = new (std::nothrow) msq_comm();          // value-initialised: every member zero
     if (!c) return (int)cudaErrorMemoryAllocation;
-    c->world = world; c->rank = rank; c->issued = 0;
-    c->box_local = nullptr; c->box_err = nullptr; c->box_static = nullptr; c->box_mapped = false; c->box_ready = false; c->box_seq = 0u; c->box_last = nullptr; c->box_pushed = nullptr; c->box_last_count = 0; c->box_pushed_count = 0;
-    for (int p = 0; p < msq::kMaxPeers; ++p) c->box_peer[p] = nullptr;
+    c->world = world; c->rank = rank;
     nccl_unique_id id;
     memcpy(&id, id128, sizeof(id));
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return (int)e; }
+    if ((e = cudaMalloc((void**)&c->ring, 2 * kRingDoubles * sizeof(double))) != cudaSuccess) { cudaStreamDestroy(c->side); delete c; return (int)e; }
+    cudaMemset(c->ring, 0, 2 * kRingDoubles * sizeof(double));
+    c->box_vec = c->ring;
+    c->box_red = c->ring + kRingDoubles;
     cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
     for (int i = 0; i < kRing; ++i) cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
     if (nccl().comm_init_rank(&c->comm, world, id, rank) != 0) {
         cudaEventDestroy(c->fork);
         for (int i = 0; i < kRing; ++i) cudaEventDestroy(c->done[i]);
         cudaStreamDestroy(c->side);
+        cudaFree(c->ring);
         delete c;
         return MSQ_E_NCCL;
     }
@@ -122,6 +148,7 @@ extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm*
 
 // Enqueue all-reduce(sum) of buf[0..count) (device fp64, in place) after everything already enqueued on
 // `stream`; returns at once.  The result may be read by work enqueued on `stream` after msq_comm_join.
+// The buffer must stay allocated and untouched until then (the collective runs on the communicator's side stream).
 extern "C" int msq_comm_allreduce_f64(msq_comm* c, double* buf, int count, msq_stream_t stream) {
     if (!c || !buf || count < 1) return MSQ_E_BADARG;
     cudaError_t e;
@@ -135,25 +162,47 @@ extern "C" int msq_comm_allreduce_f64(msq_comm* c, double* buf, int count, msq_s
 
 // Make `stream` wait for the all-reduce issued `lag` calls before the most recent one (lag 0 = the most
 // recent; no host synchronisation).  A lag of 1-2 lets a collective take more than one step without stalling
-// the kernels: the statistics it carries are only logged.
+// the kernels: the statistics it carries are only logged.  On the mailbox path lag 0 also completes the steps in flight.
+// Returns MSQ_E_PEER (once per loss) if a peer's vector did not arrive within the time-out since the last call.
 extern "C" int msq_comm_join(msq_comm* c, int lag, msq_stream_t stream) {
     if (!c || lag < 0 || lag >= kRing) return MSQ_E_BADARG;
-    if (c->box_ready && c->box_last && lag == 0) {
+    if (c->box_ready && lag == 0 && c->reduced < c->seq) {
         // peer-memory path: the newest step's vector is not pushed yet, the one before it not reduced yet
-        msq::PeerBox b = make_box(c);
-        b.cur = c->box_last;
-        b.seq = c->box_seq;
-        b.count = (short)c->box_last_count;
-        b.prev_out = c->box_pushed;
-        b.prev_count = (short)c->box_pushed_count;
-        box_flush_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b, c->box_last);
-        c->box_last = nullptr;
-        c->box_pushed = nullptr;
+        const unsigned K = c->seq;
+        msq::PeerBox b = {};
+        b.st = c->box_static;
+        if (c->pushed < K) { b.cur = vec_slot(c, K); b.seq = K; b.count = (short)c->count[K % msq::kBoxSlots]; }
+        if (K >= 2 && c->reduced < K - 1) { b.prev_out = red_slot(c, K - 1); b.prev_seq = K - 1; b.prev_count = (short)c->count[(K - 1) % msq::kBoxSlots]; }
+        box_flush_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b, K, c->count[K % msq::kBoxSlots], red_slot(c, K));
+        c->pushed = K;
+        c->reduced = K;
         MSQ_CHECK_LAUNCH();
     }
-    if (c->issued <= (unsigned long long)lag) return 0;
-    const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, c->done[(c->issued - 1 - lag) % kRing], 0);
-    return (int)e;
+    if (c->issued > (unsigned long long)lag) {
+        const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, c->done[(c->issued - 1 - lag) % kRing], 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return peer_error(c);
+}
+
+// The all-reduced statistics vector of the msq_fused_fwd_bwd step issued `lag` steps before the most recent one
+// (0 = the most recent), copied device-to-device into dst on `stream`.  It exists once two further steps have been
+// enqueued (mailboxes), or after msq_comm_join(comm, 0, stream); MSQ_E_NOTREADY otherwise.
+extern "C" int msq_comm_result(msq_comm* c, int lag, double* dst, int count, msq_stream_t stream) {
+    if (!c || !dst || lag < 0 || lag >= msq::kBoxSlots - 1 || count < 1 || count > msq::kBoxCount) return MSQ_E_BADARG;
+    if (c->seq <= (unsigned)lag) return MSQ_E_NOTREADY;
+    const unsigned k = c->seq - (unsigned)lag;
+    if (count > c->count[k % msq::kBoxSlots]) return MSQ_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->box_ready) {
+        if (c->reduced < k) return MSQ_E_NOTREADY;
+    } else if (c->world > 1) {
+        const unsigned long long idx = c->ar_index[k % msq::kBoxSlots];
+        if (c->issued - idx > (unsigned long long)kRing) return MSQ_E_NOTREADY;          // its event was recycled
+        const cudaError_t e = cudaStreamWaitEvent(s, c->done[idx % kRing], 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return (int)cudaMemcpyAsync(dst, red_slot(c, k), (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, s);
 }
 
 // ---- peer-memory mailboxes -------------------------------------------------------------------------------
@@ -166,12 +215,13 @@ extern "C" int msq_comm_box_export(msq_comm* c, void* handle64) {
     if (c->world > msq::kMaxPeers) return MSQ_E_BADARG;
     cudaError_t e;
     if (!c->box_local) {
-        constexpr size_t kTail = 16 + sizeof(msq::PeerBoxStatic);
+        constexpr size_t kTail = sizeof(msq::PeerBoxStatic);
         if ((e = cudaMalloc((void**)&c->box_local, kBoxBytes + kTail)) != cudaSuccess) return (int)e;
         if ((e = cudaMemset(c->box_local, 0, kBoxBytes + kTail)) != cudaSuccess) return (int)e;
+        if ((e = cudaHostAlloc((void**)&c->err_host, 64, cudaHostAllocMapped)) != cudaSuccess) return (int)e;
+        memset(c->err_host, 0, 64);
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
-        c->box_err = (unsigned*)((char*)c->box_local + kBoxBytes);
-        c->box_static = (msq::PeerBoxStatic*)((char*)c->box_local + kBoxBytes + 16);
+        c->box_static = (msq::PeerBoxStatic*)((char*)c->box_local + kBoxBytes);
     }
     cudaIpcMemHandle_t h;
     if ((e = cudaIpcGetMemHandle(&h, c->box_local)) != cudaSuccess) return (int)e;
@@ -191,16 +241,31 @@ extern "C" int msq_comm_box_open(msq_comm* c, const void* handles /* world x 64 
         if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
         c->box_peer[p] = (uint4*)ptr;
     }
-    msq::PeerBoxStatic st = {};
+    msq::PeerBoxStatic& st = c->box_static_host;
+    st = msq::PeerBoxStatic{};
     st.world = c->world;
     st.rank = c->rank;
-    st.err = c->box_err;
-    for (int p = 0; p < c->world; ++p) st.peer[p] = c->box_peer[p];
-    cudaError_t e = cudaMemcpy(c->box_static, &st, sizeof(st), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaHostGetDevicePointer((void**)&st.err, c->err_host, 0);
     if (e != cudaSuccess) return (int)e;
+    st.timeout_ns = default_timeout_ns();
+    for (int p = 0; p < c->world; ++p) st.peer[p] = c->box_peer[p];
+    if ((e = cudaMemcpy(c->box_static, &st, sizeof(st), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
     c->box_mapped = true;
     return 0;
+}
+
+// How long one reduction waits for a peer's vector before giving that vector up (NaN statistics for that step, MSQ_E_PEER
+// from the next msq_comm_join / msq_fused_fwd_bwd).  Default 600 s (MSQ_BOX_TIMEOUT_S), the order of NCCL's watchdog: rank
+// skew of many seconds is routine (rank-0-only validation, checkpoints, a dataloader stall).  Synchronises the device.
+extern "C" int msq_comm_box_timeout(msq_comm* c, double seconds) {
+    if (!c || !(seconds > 0.0) || !c->box_mapped) return MSQ_E_BADARG;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    c->box_static_host.timeout_ns = (unsigned long long)(seconds * 1e9);
+    e = cudaMemcpy(c->box_static, &c->box_static_host, sizeof(msq::PeerBoxStatic), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaDeviceSynchronize();
 }
 
 // Switch the mailbox path on (only if every peer is mapped) or off.  The caller enables it on all ranks or on none:
@@ -208,20 +273,24 @@ extern "C" int msq_comm_box_open(msq_comm* c, const void* handles /* world x 64 
 extern "C" int msq_comm_box_enable(msq_comm* c, int on) {
     if (!c) return MSQ_E_BADARG;
     if (on && !c->box_mapped) return MSQ_E_BADARG;
-    if (c->box_last) return MSQ_E_BADARG;          // steps in flight: msq_comm_join first
+    if (c->box_ready && c->reduced < c->seq) return MSQ_E_BADARG;          // steps in flight: msq_comm_join first
     c->box_ready = on != 0;
+    c->pushed = c->reduced = c->seq;
     return 0;
 }
 
 // 1 if msq_fused_fwd_bwd exchanges the statistics through the mailboxes, 0 if it uses ncclAllReduce
 extern "C" int msq_comm_box_active(const msq_comm* c) { return (c && c->box_ready) ? 1 : 0; }
 
-// device error word of the mailbox path (bit 0: a peer's vector never arrived); synchronises the device
+// error words of the mailbox path: *out bit 0 = a peer's vector did not arrive in time at least once; read from mapped
+// host memory after synchronising the device
 extern "C" int msq_comm_box_errors(msq_comm* c, unsigned* out) {
     if (!c || !out) return MSQ_E_BADARG;
     *out = 0u;
-    if (!c->box_err) return 0;
-    return (int)cudaMemcpy(out, c->box_err, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (!c->err_host) return 0;
+    const cudaError_t e = cudaDeviceSynchronize();
+    *out = ((volatile unsigned*)c->err_host)[0];
+    return (int)e;
 }
 
 extern "C" void msq_comm_destroy(msq_comm* c) {
@@ -233,6 +302,8 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
             if (p != c->rank && c->box_peer[p]) cudaIpcCloseMemHandle(c->box_peer[p]);
         cudaFree(c->box_local);
     }
+    if (c->err_host) cudaFreeHost(c->err_host);
+    if (c->ring) cudaFree(c->ring);
     if (c->comm) nccl().comm_destroy(c->comm);
     cudaEventDestroy(c->fork);
     for (int i = 0; i < kRing; ++i) cudaEventDestroy(c->done[i]);
@@ -246,6 +317,7 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
 // over the peer-memory mailboxes when they are open, else one ncclAllReduce forked after the backward (so that nothing
 // sits between forward -> finalise -> backward) and ordered after the collective issued `lag` steps earlier.  Same
 // kernels and results as the separate calls; it also keeps the host side of a 35 us step to one library call.
+// `out.stats` keeps this rank's LOCAL vector; the all-reduced one is kept by the communicator (msq_comm_result).
 // All steps of one communicator must be enqueued on the same stream (the mailbox protocol relies on stream order).
 extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                                  double ratio, int n_images_norm, void* accum, void* out, void* aux, const float* grad_out,
@@ -253,39 +325,47 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
     if (!grad_logits || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES) return MSQ_E_BADARG;
     if ((((uintptr_t)aux) & 15u) || (((uintptr_t)grad_logits) & 3u)) return MSQ_E_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    const msq_state_layout lay = msq::make_layout(n, num_class);
-    double* stats = (double*)((char*)out + lay.stats_off);
-    if (comm && comm->box_ready && 1 + num_class <= msq::kBoxCount) {
+    const int nstat = 1 + num_class;
+    if (comm && comm->box_ready && nstat <= msq::kBoxCount) {
         // sharded: a second CTA of this step's finalisation kernel pushes the PREVIOUS step's [loss | hist] into every
         // rank's mailbox over NVLink and reduces the step before that; nothing is enqueued between or after the three
         // kernels of the step and the hot kernels are untouched
+        const unsigned k = comm->seq + 1u;
         msq::PeerBox b = {};
-        if (comm->box_last) {
-            b = make_box(comm);
-            b.cur = comm->box_last;
-            b.seq = comm->box_seq;
-            b.count = (short)comm->box_last_count;
-            b.prev_out = comm->box_pushed;
-            b.prev_count = (short)comm->box_pushed_count;
-        }
+        b.st = comm->box_static;
+        b.keep = vec_slot(comm, k);
+        b.keep_count = (short)nstat;
+        if (k >= 2 && comm->pushed < k - 1) { b.cur = vec_slot(comm, k - 1); b.seq = k - 1; b.count = (short)comm->count[(k - 1) % msq::kBoxSlots]; }
+        if (k >= 3 && comm->reduced < k - 2) { b.prev_out = red_slot(comm, k - 2); b.prev_seq = k - 2; b.prev_count = (short)comm->count[(k - 2) % msq::kBoxSlots]; }
         int rc = msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum,
                                          out, aux, grad_logits, s, 0, &b);
         if (rc) return rc;
-        comm->box_pushed = comm->box_last;
-        comm->box_pushed_count = comm->box_last_count;
-        comm->box_last = stats;
-        comm->box_last_count = 1 + num_class;
-        comm->box_seq += 1u;
-        return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
-                                       grad_logits, aux, 1, s);
+        comm->seq = k;
+        comm->count[k % msq::kBoxSlots] = nstat;
+        if (b.cur) comm->pushed = k - 1;
+        if (b.prev_out) comm->reduced = k - 2;
+        rc = msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
+                                     grad_logits, aux, 1, s);
+        return rc ? rc : peer_error(comm);
     }
     int rc = msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum, out,
                                      aux, grad_logits, s);
     if (rc) return rc;
     rc = msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
                                  grad_logits, aux, 1, s);
-    if (rc || !comm) return rc;
+    if (rc || !comm || nstat > msq::kBoxCount) return rc;
+    // NCCL path: the vector is copied into the communicator's ring on the caller's stream (after the backward: nothing
+    // between the step's kernels) and all-reduced THERE on the side stream; the caller's `out` is never touched later
+    const msq_state_layout lay = msq::make_layout(n, num_class);
+    const unsigned k = comm->seq + 1u;
+    cudaError_t e = cudaMemcpyAsync(red_slot(comm, k), (const char*)out + lay.stats_off, (size_t)nstat * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    comm->seq = k;
+    comm->count[k % msq::kBoxSlots] = nstat;
+    if (comm->world == 1) return 0;
     rc = msq_comm_join(comm, lag, stream);
     if (rc) return rc;
-    return msq_comm_allreduce_f64(comm, stats, 1 + num_class, stream);
+    comm->ar_index[k % msq::kBoxSlots] = comm->issued;
+    return msq_comm_allreduce_f64(comm, red_slot(comm, k), nstat, stream);
 }

@@ -10,7 +10,7 @@
 
 namespace msq {
 
-constexpr int kSMs = 148;                       // B200: 2 dies x 74 SMs
+constexpr int kSMs = 148;                       // B200: 2 dies x 74 SMs (fallback only: sm_count() asks the device)
 constexpr float kFix = 4294967296.0f;           // 2^32: fixed-point scale of q = sum_c p_c^2
 constexpr double kInvFix = 1.0 / 4294967296.0;
 constexpr unsigned kFlagNonFinite = 1u;
@@ -39,6 +39,25 @@ struct State {
     unsigned long long* nvalid_out;
     double* ce_out;                // out: sum of -log p2[label_2] over the valid pixels (for sharded means)
 };
+
+// SM count of the CURRENT device (a process may drive several GPUs: cached per ordinal)
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev;
+}
+inline int sm_count() {
+    constexpr int kMaxDev = 64;
+    static int cache[kMaxDev] = {0};
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDev) return kSMs;
+    int n = cache[dev];
+    if (!n) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
+        cache[dev] = n;
+    }
+    return n;
+}
 
 __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -188,17 +207,20 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
         const int idx = img * C + lane;
         unsigned hcnt = 0u;
         unsigned long long sq = 0ull;
+        double sd = 0.0;
         if (lane < C) {
 #pragma unroll
             for (int r = 0; r < kRep; ++r) {          // independent loads: one latency
                 hcnt += __ldcg(&st.hist[r * nc + idx]);          // L2: other CTAs' atomics (fused step kernel)
-                sq += __ldcg(&st.sumsq[r * nc + idx]);
+                const unsigned long long v = __ldcg(&st.sumsq[r * nc + idx]);
+                if (loss_kind == 2) sd += __longlong_as_double((long long)v);      // strict MinEnt (softce.cu): fp64 sums
+                else sq += v;
             }
 #pragma unroll
             for (int r = 0; r < kRep; ++r) { st.hist[r * nc + idx] = 0u; st.sumsq[r * nc + idx] = 0ull; }   // self-clean
         }
         const unsigned total = __reduce_add_sync(0xffffffffu, hcnt);
-        const double S = (double)sq * kInvFix;
+        const double S = (loss_kind == 2) ? sd : (double)sq * kInvFix;
         float wgt = 1.0f;
         if (mode == MSQ_MODE_IW && lane < C) wgt = iw_weight((float)hcnt, (float)total, r32, omr32);
         if (lane < C) {
@@ -268,23 +290,33 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
 constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch box
 constexpr int kBoxSlots = 8;       // ring of sequence numbers: when vector s is pushed, vectors s-3 .. s-1 may still be read (>= 4 slots)
 constexpr int kBoxCount = 40;      // doubles per vector (1 + 32 classes, rounded up)
-constexpr unsigned kBoxSpinLimit = 1u << 24;     // polls (~0.8 us each) before a cell is declared lost: ~13 s, never a hung GPU
 
 // Static part, resident in device memory (written once by msq_comm_box_open).
 struct PeerBoxStatic {
     int world, rank;
-    unsigned* err;                 // local error word: bit 0 = a peer's cell never arrived
+    unsigned* err;                 // error words in MAPPED PINNED HOST memory (the host reads them without synchronising):
+                                   //   [0] bit 0 = some peer's vector did not arrive in time, [1] = how many vectors were lost
+    unsigned long long timeout_ns; // how long one reduction waits for a peer (msq_comm_box_timeout; default 600 s, the order of
+                                   // NCCL's watchdog).  Re-armed for every vector: a late peer costs NaN statistics for the
+                                   // vectors it missed, not for the rest of the run
     uint4* peer[kMaxPeers];        // rank p's mailbox: [kBoxSlots][kMaxPeers][kBoxCount] cells (peer[rank] is local)
 };
-// Per-step part, passed to the kernel by value (32 bytes of parameters; st == NULL: no exchange).
+// Per-step part, passed to the kernel by value (st == NULL: no exchange).  Every pointer is into memory the COMMUNICATOR
+// owns (msq_comm: box_vec / box_red rings): nothing here outlives or aliases a caller's buffer.
 struct PeerBox {
     const PeerBoxStatic* st;
-    const double* cur;             // the vector to push: this rank's statistics of sequence number `seq` (NULL: none)
-    double* prev_out;              // where the all-reduced vector of sequence number seq-1 goes (NULL: nothing to reduce)
-    unsigned seq;                  // 1, 2, ...; 0 is never used (it is the flag value of an empty cell)
-    short count, prev_count;       // doubles in the pushed / the reduced vector
+    const double* cur;             // vector to push: this rank's statistics of sequence number `seq` (NULL: nothing to push)
+    double* prev_out;              // where the all-reduced vector of sequence number `prev_seq` goes (NULL: nothing to reduce)
+    double* keep;                  // where the finalisation proper stores this step's own vector for a later push (NULL: no)
+    unsigned seq, prev_seq;        // 1, 2, ...; 0 is never used (it is the flag value of an empty cell)
+    short count, prev_count, keep_count;       // doubles per vector
 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void ll_store(uint4* cell, double v, unsigned flag) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
@@ -300,38 +332,49 @@ __device__ __forceinline__ bool ll_load(const uint4* cell, unsigned flag, double
 __device__ __forceinline__ uint4* box_cell(uint4* base, unsigned seq, int src_rank, int k) {
     return base + ((size_t)(seq % kBoxSlots) * kMaxPeers + src_rank) * kBoxCount + k;
 }
-// sum over the ranks, in rank order (identical bits on every rank), of the vectors pushed for `seq`
+// sum over the ranks, in rank order (identical bits on every rank), of the vectors pushed for `seq`.  One warp.
 __device__ __forceinline__ void box_reduce(const PeerBoxStatic* st, unsigned seq, int count, double* out, int lane) {
     const int world = st->world, rank = st->rank;
     uint4* mine = st->peer[rank];
-    // the error is sticky: once a peer's vector has been declared lost, no later call waits again (a dead peer costs
-    // ONE time-out, not one per step)
-    bool lost = (*(volatile unsigned*)st->err & 1u) != 0u;
+    const unsigned long long limit = st->timeout_ns;
+    unsigned long long t0 = 0ull;
+    bool lost = false;
     for (int k = lane; k < count; k += 32) {
         double sum = 0.0;
         for (int p = 0; p < world; ++p) {
             const uint4* cell = box_cell(mine, seq, p, k);
             double v = 0.0;
             unsigned spins = 0;
-            while (!ll_load(cell, seq, v)) {
-                if (lost || ++spins > kBoxSpinLimit) { lost = true; v = __longlong_as_double(0x7ff8000000000000LL); break; }
+            while (!lost && !ll_load(cell, seq, v)) {
+                if ((++spins & 255u) == 0u) {                     // look at the clock every 256 polls
+                    const unsigned long long now = global_ns();
+                    if (t0 == 0ull) t0 = now;
+                    else if (now - t0 > limit) lost = true;       // this vector is given up; the next one waits afresh
+                }
                 __nanosleep(64);
             }
+            if (lost) v = __longlong_as_double(0x7ff8000000000000LL);
             sum += v;
         }
         out[k] = sum;
     }
-    if (lost) atomicOr(st->err, 1u);
-}
-// One warp: push vector `seq` to every rank (itself included), then reduce vector seq-1.
-__device__ __forceinline__ void box_exchange(const PeerBoxStatic* st, const double* cur, double* prev_out, unsigned seq,
-                                          int count, int prev_count, int lane) {
-    const int world = st->world, rank = st->rank;
-    for (int k = lane; cur && k < count; k += 32) {
-        const double v = cur[k];
-        for (int p = 0; p < world; ++p) ll_store(box_cell(st->peer[p], seq, rank, k), v, seq);
+    if (__any_sync(0xffffffffu, lost) && lane == 0) {             // one warp per GPU ever writes these words
+        volatile unsigned* e = st->err;
+        e[0] = e[0] | 1u;
+        e[1] = e[1] + 1u;
     }
-    if (prev_out) box_reduce(st, seq - 1u, prev_count, prev_out, lane);
+}
+// One warp: push vector `seq` to every rank (itself included), then reduce vector `prev_seq`.
+__device__ __forceinline__ void box_exchange(const PeerBox& b, int lane) {
+    const PeerBoxStatic* st = b.st;
+    if (b.cur) {
+        const int world = st->world, rank = st->rank;
+        for (int k = lane; k < b.count; k += 32) {
+            const double v = b.cur[k];
+            for (int p = 0; p < world; ++p) ll_store(box_cell(st->peer[p], b.seq, rank, k), v, b.seq);
+        }
+    }
+    if (b.prev_out) box_reduce(st, b.prev_seq, b.prev_count, b.prev_out, lane);
 }
 
 // Finalisation kernel (api.cu), launched on the same stream right after a forward kernel:

@@ -159,7 +159,7 @@ __device__ __forceinline__ void argmax_step(float v, int c, float& best, int& ar
 template <int CT, int AGG, bool VEC>
 __global__ void __launch_bounds__(kConfThreads)
 confusion_logits_kernel(const int64_t* __restrict__ gt, const float* __restrict__ logits, int C, long long hw,
-                        unsigned long long* __restrict__ cm) {
+                        unsigned long long* __restrict__ cm, long long cm_stride, unsigned long long* __restrict__ total) {
     extern __shared__ unsigned s_cm[];
     const int nbins = C * C;
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_cm[b] = 0u;
@@ -238,7 +238,78 @@ confusion_logits_kernel(const int64_t* __restrict__ gt, const float* __restrict_
         }
     }
     __syncthreads();
-    merge_to_global(s_cm, nbins, cm);
+    merge_to_global(s_cm, nbins, cm + (long long)n * cm_stride);       // cm_stride > 0: one matrix per image (tools/analysis.py:200-229)
+    if (total) merge_to_global(s_cm, nbins, total);
+}
+
+// ------------------------------------------------------------------ K5c: K (gt, pred) pairs in ONE launch
+// The reference's evaluation loops call Eval.add_batch once per image (tools/train_source.py:429-492,
+// tools/evaluate.py:99-202, tools/analysis.py:200-229): one 8 MB launch each is launch/drain bound (33 % of HBM).
+// Here up to kConfJobs pairs ride in the kernel parameters; the CTAs split the CONCATENATION of all pairs' 4-pixel
+// groups evenly (one balanced wave whatever the image sizes) and merge their shared-memory histogram at every pair
+// boundary they cross: into ONE matrix (cm_stride = 0: K deferred add_batch calls) or into one matrix per pair
+// (cm_stride >= C*C: the per-image evaluation of tools/analysis.py), and optionally into a running total as well.
+constexpr int kConfJobs = 32;
+struct ConfJobs {
+    const int64_t* gt[kConfJobs];
+    const int64_t* pred[kConfJobs];
+    long long npix[kConfJobs];
+    long long first[kConfJobs + 1];      // first[j] = number of 4-pixel groups of pairs 0..j-1
+    int k;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(kConfBig, 1)
+confusion_multi_kernel(const ConfJobs jobs, int C, unsigned long long* __restrict__ cm, long long cm_stride,
+                       unsigned long long* __restrict__ total, unsigned* __restrict__ errs) {
+    extern __shared__ unsigned s_all[];
+    const int nbins = C * C;
+    for (int b = threadIdx.x; b < nbins * kConfSub; b += blockDim.x) s_all[b] = 0u;
+    unsigned* s_cm = s_all + (threadIdx.x >> 8) * nbins;
+    __syncthreads();
+    pdl_trigger();
+    pdl_wait();
+    const long long G = jobs.first[jobs.k];
+    const long long g0 = G * blockIdx.x / gridDim.x, g1 = G * (blockIdx.x + 1) / gridDim.x;
+    int j = 0;
+    while (j < jobs.k && jobs.first[j + 1] <= g0) ++j;
+    for (; j < jobs.k && jobs.first[j] < g1; ++j) {
+        const long long lo = max(g0, jobs.first[j]) - jobs.first[j], hi = min(g1, jobs.first[j + 1]) - jobs.first[j];
+        const int64_t* __restrict__ gt = jobs.gt[j];
+        const int64_t* __restrict__ pr = jobs.pred[j];
+        const long long npix = jobs.npix[j];
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            long long g[4], p[4];
+            int b[4];
+            if (VEC && 4 * i + 3 < npix) {
+                const longlong2 ga = ldg_stream_l2(gt + 4 * i), gb = ldg_stream_l2(gt + 4 * i + 2);
+                const longlong2 pa = ldg_stream_l2(pr + 4 * i), pb = ldg_stream_l2(pr + 4 * i + 2);
+                g[0] = ga.x; g[1] = ga.y; g[2] = gb.x; g[3] = gb.y;
+                p[0] = pa.x; p[1] = pa.y; p[2] = pb.x; p[3] = pb.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool in = 4 * i + q < npix;
+                    g[q] = in ? ldg_stream_l1(gt + 4 * i + q) : -1;
+                    p[q] = in ? ldg_stream_l1(pr + 4 * i + q) : 0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b[q] = conf_bin(g[q], p[q], C, errs);
+            add_four<0>(s_cm, b[0], b[1], b[2], b[3]);
+        }
+        const bool last = (j + 1 >= jobs.k) || (jobs.first[j + 1] >= g1);
+        if (cm_stride == 0 && !last) continue;            // one matrix for all pairs: merge once, at the end
+        __syncthreads();
+        unsigned long long* dst = cm + (long long)j * cm_stride;
+        for (int bb = threadIdx.x; bb < nbins; bb += blockDim.x) {
+            unsigned long long v = 0ull;
+#pragma unroll
+            for (int s = 0; s < kConfSub; ++s) { v += s_all[s * nbins + bb]; s_all[s * nbins + bb] = 0u; }
+            if (v) { atomicAdd(&dst[bb], v); if (total) atomicAdd(&total[bb], v); }
+        }
+        __syncthreads();
+    }
 }
 
 int g_conf_ctas_per_sm = 1;   // tuning knob: 1024-thread CTAs per SM for the int64 kernel (1 or 2)
@@ -253,7 +324,7 @@ static int launch_i64(const int64_t* gt, const int64_t* pred, long long npix, in
     const bool vec = ((((uintptr_t)gt) | ((uintptr_t)pred)) & 15u) == 0;
     const long long groups = (npix + 3) / 4;
     long long blocks = (groups + kConfBig - 1) / kConfBig;
-    const long long cap = (long long)kSMs * (g_conf_ctas_per_sm > 0 ? g_conf_ctas_per_sm : 1);
+    const long long cap = (long long)sm_count() * (g_conf_ctas_per_sm > 0 ? g_conf_ctas_per_sm : 1);
     if (blocks > cap) blocks = cap;
     if (g_conf_grid > 0 && blocks > g_conf_grid) blocks = g_conf_grid;
     if (blocks < 1) blocks = 1;
@@ -268,19 +339,19 @@ static int launch_i64(const int64_t* gt, const int64_t* pred, long long npix, in
 
 template <int CT, int AGG>
 static int launch_logits(const int64_t* gt, const float* logits, int n, int C, long long hw, unsigned long long* cm,
-                         cudaStream_t st) {
+                         cudaStream_t st, long long cm_stride = 0, unsigned long long* total = nullptr) {
     const bool vec = ((hw & 3) == 0) && (((uintptr_t)gt & 15u) == 0) && (((uintptr_t)logits & 15u) == 0);
     const long long groups = (hw + 3) / 4;
     long long bx = (groups + kConfThreads - 1) / kConfThreads;
     // CT>0 keeps CT float4 in registers (~100 regs): 2 CTAs of 256 threads per SM
-    const long long cap = ((long long)kSMs * (CT > 0 ? 2 : 4) * 2 + n - 1) / n;   // ~2 waves over all images
+    const long long cap = ((long long)sm_count() * (CT > 0 ? 2 : 4) * 2 + n - 1) / n;   // ~2 waves over all images
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     const dim3 grid((unsigned)bx, (unsigned)n);
     const size_t smem = (size_t)C * C * sizeof(unsigned);
     cudaError_t le;
-    if (vec) le = launch_pdl(confusion_logits_kernel<CT, AGG, true>, grid, dim3(kConfThreads), smem, st, gt, logits, C, hw, cm);
-    else le = launch_pdl(confusion_logits_kernel<0, AGG, false>, grid, dim3(kConfThreads), smem, st, gt, logits, C, hw, cm);
+    if (vec) le = launch_pdl(confusion_logits_kernel<CT, AGG, true>, grid, dim3(kConfThreads), smem, st, gt, logits, C, hw, cm, cm_stride, total);
+    else le = launch_pdl(confusion_logits_kernel<0, AGG, false>, grid, dim3(kConfThreads), smem, st, gt, logits, C, hw, cm, cm_stride, total);
     if (le != cudaSuccess) return (int)le;
     MSQ_CHECK_LAUNCH();
     return 0;
@@ -304,19 +375,19 @@ extern "C" int msq_confusion_i64(const int64_t* gt, const int64_t* pred, int64_t
     }
 }
 
-extern "C" int msq_confusion_logits_f32(const int64_t* gt, const float* logits, int n, int num_class, int64_t hw,
-                                        unsigned long long* cm, msq_stream_t stream) {
+static int confusion_logits_dispatch(const int64_t* gt, const float* logits, int n, int num_class, int64_t hw,
+                                     unsigned long long* cm, long long cm_stride, unsigned long long* total, msq_stream_t stream) {
     if (!cm || num_class < 1 || num_class > MSQ_MAX_CLASSES || n < 0 || hw < 0) return MSQ_E_BADARG;
     if (n == 0 || hw == 0) return 0;
     if (!gt || !logits) return MSQ_E_BADARG;
-    if ((((uintptr_t)gt) | ((uintptr_t)cm)) & 7u) return MSQ_E_ALIGN;
+    if ((((uintptr_t)gt) | ((uintptr_t)cm) | ((uintptr_t)total)) & 7u) return MSQ_E_ALIGN;
     if (((uintptr_t)logits) & 3u) return MSQ_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int agg = g_conf_agg;
-#define MSQ_DISPATCH_CT(CT)                                                                  \
-    (agg == 0 ? launch_logits<CT, 0>(gt, logits, n, num_class, hw, cm, st)                   \
-              : agg == 2 ? launch_logits<CT, 2>(gt, logits, n, num_class, hw, cm, st)        \
-                         : launch_logits<CT, 1>(gt, logits, n, num_class, hw, cm, st))
+#define MSQ_DISPATCH_CT(CT)                                                                                  \
+    (agg == 0 ? launch_logits<CT, 0>(gt, logits, n, num_class, hw, cm, st, cm_stride, total)                 \
+              : agg == 2 ? launch_logits<CT, 2>(gt, logits, n, num_class, hw, cm, st, cm_stride, total)      \
+                         : launch_logits<CT, 1>(gt, logits, n, num_class, hw, cm, st, cm_stride, total))
     switch (num_class) {
         case 13: return MSQ_DISPATCH_CT(13);
         case 16: return MSQ_DISPATCH_CT(16);
@@ -324,4 +395,57 @@ extern "C" int msq_confusion_logits_f32(const int64_t* gt, const float* logits, 
         default: return MSQ_DISPATCH_CT(0);
     }
 #undef MSQ_DISPATCH_CT
+}
+
+extern "C" int msq_confusion_logits_f32(const int64_t* gt, const float* logits, int n, int num_class, int64_t hw,
+                                        unsigned long long* cm, msq_stream_t stream) {
+    return confusion_logits_dispatch(gt, logits, n, num_class, hw, cm, 0, nullptr, stream);
+}
+
+extern "C" int msq_confusion_per_image_logits_f32(const int64_t* gt, const float* logits, int n, int num_class, int64_t hw,
+                                                  unsigned long long* cm_per_image, unsigned long long* total,
+                                                  msq_stream_t stream) {
+    return confusion_logits_dispatch(gt, logits, n, num_class, hw, cm_per_image, (long long)num_class * num_class, total, stream);
+}
+
+extern "C" int msq_confusion_i64_multi(const int64_t* const* gt, const int64_t* const* pred, const int64_t* npix, int k,
+                                       int num_class, unsigned long long* cm, int64_t cm_stride, unsigned long long* total,
+                                       unsigned int* errs, msq_stream_t stream) {
+    if (!cm || num_class < 1 || num_class > MSQ_MAX_CLASSES || k < 0) return MSQ_E_BADARG;
+    if (cm_stride != 0 && cm_stride < (int64_t)num_class * num_class) return MSQ_E_BADARG;
+    if (k == 0) return 0;
+    if (!gt || !pred || !npix) return MSQ_E_BADARG;
+    if ((((uintptr_t)cm) | ((uintptr_t)total)) & 7u) return MSQ_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)num_class * num_class * sizeof(unsigned) * kConfSub;
+    for (int base = 0; base < k; base += kConfJobs) {          // kConfJobs pairs per launch (they travel as kernel parameters)
+        ConfJobs jobs;
+        jobs.k = 0;
+        jobs.first[0] = 0;
+        bool vec = true;
+        for (int j = base; j < k && jobs.k < kConfJobs; ++j) {
+            if (npix[j] < 0) return MSQ_E_BADARG;
+            if (npix[j] == 0) continue;
+            if (!gt[j] || !pred[j]) return MSQ_E_BADARG;
+            if ((((uintptr_t)gt[j]) | ((uintptr_t)pred[j])) & 7u) return MSQ_E_ALIGN;
+            if ((((uintptr_t)gt[j]) | ((uintptr_t)pred[j])) & 15u) vec = false;
+            const int q = jobs.k++;
+            // with per-pair matrices the output slot is the pair's index in the caller's table
+            jobs.gt[q] = gt[j]; jobs.pred[q] = pred[j]; jobs.npix[q] = npix[j];
+            jobs.first[q + 1] = jobs.first[q] + (npix[j] + 3) / 4;
+            if (cm_stride != 0 && q != j - base) return MSQ_E_BADARG;      // empty pairs are not allowed in per-pair mode
+        }
+        if (jobs.k == 0) continue;
+        long long blocks = (jobs.first[jobs.k] + kConfBig - 1) / kConfBig;
+        const long long cap = (long long)sm_count() * (g_conf_ctas_per_sm > 0 ? g_conf_ctas_per_sm : 1);
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        unsigned long long* dst = cm + (long long)base * cm_stride;
+        cudaError_t le;
+        if (vec) le = launch_pdl(confusion_multi_kernel<true>, dim3((unsigned)blocks), dim3(kConfBig), smem, st, jobs, num_class, dst, (long long)cm_stride, total, errs);
+        else le = launch_pdl(confusion_multi_kernel<false>, dim3((unsigned)blocks), dim3(kConfBig), smem, st, jobs, num_class, dst, (long long)cm_stride, total, errs);
+        if (le != cudaSuccess) return (int)le;
+        MSQ_CHECK_LAUNCH();
+    }
+    return 0;
 }

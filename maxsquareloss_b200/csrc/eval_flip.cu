@@ -215,7 +215,7 @@ static int launch_flip(const int64_t* gt, const float* la, const float* lb, int 
     if (CT > 0 && flip_px() == 2 && (W & 1) == 0 && ((((uintptr_t)la) | ((uintptr_t)lb)) & 7u) == 0 && (((uintptr_t)gt) & 15u) == 0) {
         const long long npairs = hw / 2;
         long long b2 = (npairs + kFlipThreads - 1) / kFlipThreads;
-        const long long cap2 = ((long long)kSMs * 2 + n - 1) / n;          // one persistent wave over all images
+        const long long cap2 = ((long long)sm_count() * 2 + n - 1) / n;          // one persistent wave over all images
         if (b2 > cap2) b2 = cap2;
         if (b2 < 1) b2 = 1;
         const cudaError_t le2 = launch_pdl(confusion_flip2_kernel<(CT > 0 ? CT : 1)>, dim3((unsigned)b2, (unsigned)n), dim3(kFlipThreads),
@@ -225,7 +225,7 @@ static int launch_flip(const int64_t* gt, const float* la, const float* lb, int 
         return 0;
     }
     long long bx = (hw + kFlipThreads - 1) / kFlipThreads;
-    const long long cap = ((long long)kSMs * 2 * 4 + n - 1) / n;      // a few waves over all images
+    const long long cap = ((long long)sm_count() * 2 * 4 + n - 1) / n;      // a few waves over all images
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     const cudaError_t le = launch_pdl(confusion_flip_kernel<CT>, dim3((unsigned)bx, (unsigned)n), dim3(kFlipThreads),

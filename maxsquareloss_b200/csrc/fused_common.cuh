@@ -770,16 +770,6 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
 extern int g_fused_rows;   // tuning knob (fused_loss.cu): 0 = automatic (one balanced wave), R = about R rows per CTA
 extern int g_reserve_sms;  // SMs left free by the one-wave grids (for a concurrent NCCL kernel when sharded)
 
-static inline int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
-    }
-    return n;
-}
-
 struct Plan {
     FusedGeo g;
     long long units;
@@ -869,9 +859,10 @@ struct LaunchPlan {
 };
 struct PlanKey {
     const void* kernel;
-    int C, h, w, H, W, n, rows;
+    int C, h, w, H, W, n, rows, device;      // device: the SM count and the shared-memory opt-in are per device
     bool operator==(const PlanKey& o) const {
-        return kernel == o.kernel && C == o.C && h == o.h && w == o.w && H == o.H && W == o.W && n == o.n && rows == o.rows;
+        return kernel == o.kernel && C == o.C && h == o.h && w == o.w && H == o.H && W == o.W && n == o.n && rows == o.rows &&
+               device == o.device;
     }
 };
 static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
@@ -894,7 +885,7 @@ static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
 // plan + shared-memory size for `kernel`, compiled for `minb` co-resident CTAs per SM
 template <typename K, typename SmemFn>
 static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp) {
-    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows + 100000 * g_reserve_sms};
+    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows + 100000 * g_reserve_sms, current_device()};
     if (plan_cache(key, lp, false)) return 0;
     int rc = make_plan(C, h, w, H, W, n, minb, lp.p);
     if (rc) return rc;

@@ -245,7 +245,7 @@ static dim3 stream_grid(long long hw, int n, int px, int ctas_per_sm) {
     // epilogue (bucket reduction, global atomics) is amortised over many pixel groups
     const long long groups = (hw + px - 1) / px;
     long long bx = (groups + kProbThreads - 1) / kProbThreads;
-    const long long cap = ((long long)kSMs * ctas_per_sm * (g_prob_waves > 0 ? g_prob_waves : 1) + n - 1) / n;
+    const long long cap = ((long long)sm_count() * ctas_per_sm * (g_prob_waves > 0 ? g_prob_waves : 1) + n - 1) / n;
     if (bx > cap) bx = cap;
     const long long need = (groups + (long long)kProbThreads * 8192 - 1) / ((long long)kProbThreads * 8192);
     if (bx < need) bx = need;          // packed 16-bit per-thread pixel counts: <= 8192 groups per thread

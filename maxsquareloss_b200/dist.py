@@ -131,6 +131,21 @@ class StatsComm:
         self._libmod.check(self._lib.msq_comm_box_errors(self._h, ctypes.byref(v)))
         return int(v.value)
 
+    def set_timeout(self, seconds):
+        """How long a mailbox reduction waits for a peer's vector (default 600 s).  Synchronises the device."""
+        self._libmod.check(self._lib.msq_comm_box_timeout(self._h, float(seconds)))
+
+    def result(self, count, lag=0, out=None, stream=None):
+        """All-reduced ``[loss | class hist]`` (``count`` = 1 + C doubles) of the ``msq_fused_fwd_bwd`` step issued ``lag``
+        steps before the most recent one, as a float64 CUDA tensor (device-to-device copy on the current stream).  It exists
+        once two further steps have been enqueued, or after ``join()``."""
+        if out is None:
+            out = torch.empty(count, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        self._libmod.check(self._lib.msq_comm_result(self._h, int(lag), out.data_ptr(), int(count), stream))
+        return out
+
     def allreduce(self, buf):
         """Sum the float64 CUDA vector ``buf`` over the ranks, in place, asynchronously w.r.t. the current stream."""
         if not (buf.is_cuda and buf.dtype == torch.float64 and buf.is_contiguous()):

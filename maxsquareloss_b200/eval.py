@@ -10,12 +10,14 @@ folded into the float64 ``confusion_matrix`` attribute when it (or any metric)
 is read; the metrics themselves are the reference's NumPy expressions on that
 float64 matrix, so they are bit-identical.
 """
+import ctypes
 import warnings
 
 import numpy as np
 import torch
 
 from . import _lib
+from .loss import _raw_stream
 
 #: class names the reference prints (datasets/cityscapes_Dataset.py:379-400)
 name_classes = ['road', 'sidewalk', 'building', 'wall', 'fence', 'pole', 'trafflight', 'traffsign',
@@ -31,6 +33,8 @@ def _to_device_labels(a, device, num_class, is_gt):
     """numpy / tensor label map -> contiguous int64 CUDA tensor with the reference's
     conversions: float ground truth is range-checked as float, then truncated
     (``gt_image[mask].astype('int')``, utils/eval.py:111-112)."""
+    if isinstance(a, torch.Tensor) and a.dtype == torch.int64 and a.is_cuda and a.device == device:
+        return a if a.is_contiguous() else a.contiguous()           # what a CUDA caller passes: nothing to convert
     t = torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a
     if t.device != device:
         if t.device.type == "cpu" and t.numel() > 0:
@@ -52,7 +56,17 @@ def _to_device_labels(a, device, num_class, is_gt):
 
 
 class Eval:
-    def __init__(self, num_class, device=None):
+    """``Eval(num_class)`` of ``utils/eval.py``.  Extra, all optional:
+
+    :param device: CUDA device of the accumulator (default: the current one)
+    :param defer:  K > 0: ``add_batch`` calls with CUDA tensors are QUEUED and run K at a time in ONE launch
+                   (``msq_confusion_i64_multi``): the reference's validation loops call ``add_batch`` once per image
+                   (``tools/train_source.py:429-492``), and one 8 MB launch per image is launch-bound.  The queue is
+                   flushed when it holds K pairs and whenever the matrix or a metric is read.  The queued tensors
+                   must not be modified in place before that (checked: a changed ``_version`` raises).
+    """
+
+    def __init__(self, num_class, device=None, defer=0):
         if not torch.cuda.is_available():
             raise RuntimeError("maxsquareloss_b200.Eval needs a CUDA device: there is no CPU fallback")
         if num_class < 1 or num_class > _lib.MAX_CLASSES:
@@ -66,6 +80,13 @@ class Eval:
         # [C*C counts | 2 error flags (as one int64: two uint32)]
         self._dev = torch.zeros(num_class * num_class + 1, dtype=torch.int64, device=self.device)
         self._pending = False
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._cm_ptr = self._dev.data_ptr()
+        self._err_ptr = self._cm_ptr + 8 * num_class * num_class
+        self._call = _lib.load().msq_confusion_i64
+        self.defer = int(defer)
+        self._queue = []                 # deferred (gt, pred, gt._version, pred._version)
+        self._per_image = []             # device blocks (k, C*C) int64 of add_batch_per_image, in call order
 
     # ------------------------------------------------------------------ accumulate
     def add_batch(self, gt_image, pre_image):
@@ -80,14 +101,94 @@ class Eval:
                          isinstance(pre_image, torch.Tensor) and pre_image.is_cuda)
         gt = _to_device_labels(gt_image, self.device, self.num_class, True)
         pr = _to_device_labels(pre_image, self.device, self.num_class, False)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        cm_ptr = self._dev.data_ptr()
-        _lib.check(_lib.load().msq_confusion_i64(gt.data_ptr(), pr.data_ptr(), gt.numel(), self.num_class,
-                                                 cm_ptr, cm_ptr + 8 * self.num_class ** 2, stream))
+        if self.defer > 0 and not host_call:
+            self._queue.append((gt, pr, gt._version, pr._version))
+            if len(self._queue) >= self.defer:
+                self._flush_queue()
+            return
+        rc = self._call(gt.data_ptr(), pr.data_ptr(), gt.numel(), self.num_class, self._cm_ptr, self._err_ptr,
+                        _raw_stream(self._dev_index))
+        if rc:
+            _lib.check(rc)
         self._pending = True
         if host_call:
             # numpy callers get the reference's synchronous behaviour, incl. ValueError now
             self._fold()
+
+    def _launch_multi(self, pairs, cm_ptr, cm_stride, total_ptr):
+        """One launch for ``pairs`` = [(gt, pred), ...] (C ABI ``msq_confusion_i64_multi``)."""
+        k = len(pairs)
+        arr = ctypes.c_void_p * k
+        gts = arr(*[p[0].data_ptr() for p in pairs])
+        prs = arr(*[p[1].data_ptr() for p in pairs])
+        npx = (ctypes.c_int64 * k)(*[p[0].numel() for p in pairs])
+        _lib.check(_lib.load().msq_confusion_i64_multi(gts, prs, npx, k, self.num_class, cm_ptr, cm_stride, total_ptr,
+                                                       self._err_ptr, _raw_stream(self._dev_index)))
+        self._pending = True
+
+    def _flush_queue(self):
+        if not self._queue:
+            return
+        q, self._queue = self._queue, []
+        for gt, pr, vg, vp in q:
+            if gt._version != vg or pr._version != vp:
+                raise RuntimeError("Eval(defer=K): a tensor handed to add_batch was modified in place before the queued "
+                                   "launch ran; pass fresh tensors or read a metric / call flush() first")
+        self._launch_multi(q, self._cm_ptr, 0, None)
+
+    def flush(self):
+        """Run the queued ``add_batch`` calls now (``defer`` > 0); no host synchronisation."""
+        self._flush_queue()
+
+    def add_batch_per_image(self, gt_image, pre_image):
+        """``add_batch`` that ALSO keeps one confusion matrix per image of the batch: what ``tools/analysis.py:200-229``
+        obtains with ``Eval.add_batch`` / metrics / ``Eval.reset()`` per image next to ``totalEval.add_batch``, in ONE
+        launch for the whole batch and without a host round trip per image.  ``pre_image``: (N,H,W) class ids or
+        float32 CUDA logits (N,C,H,W).  Read the results with ``per_image_matrices()`` / ``per_image_metrics()``."""
+        c2 = self.num_class ** 2
+        self._flush_queue()
+        if isinstance(pre_image, torch.Tensor) and pre_image.is_floating_point() and pre_image.dim() == np.ndim(gt_image) + 1:
+            if not (pre_image.is_cuda and pre_image.dtype == torch.float32):
+                raise RuntimeError("logits must be a float32 CUDA tensor (N,C,H,W)")
+            n, c = pre_image.shape[0], pre_image.shape[1]
+            assert tuple(gt_image.shape) == (n,) + tuple(pre_image.shape[2:])
+            if c != self.num_class:
+                raise ValueError(f"logits have {c} classes, Eval was built with {self.num_class}")
+            gt = _to_device_labels(gt_image, self.device, self.num_class, True)
+            lg = pre_image.contiguous()
+            block = torch.zeros(n, c2, dtype=torch.int64, device=self.device)
+            _lib.check(_lib.load().msq_confusion_per_image_logits_f32(
+                gt.data_ptr(), lg.data_ptr(), n, c, lg.numel() // max(n * c, 1), block.data_ptr(), self._cm_ptr,
+                _raw_stream(self._dev_index)))
+            self._pending = True
+        else:
+            assert tuple(gt_image.shape) == tuple(pre_image.shape)          # utils/eval.py:119
+            gt = _to_device_labels(gt_image, self.device, self.num_class, True)
+            pr = _to_device_labels(pre_image, self.device, self.num_class, False)
+            n = gt.shape[0] if gt.dim() == 3 else 1
+            g2, p2 = gt.reshape(n, -1), pr.reshape(n, -1)
+            block = torch.zeros(n, c2, dtype=torch.int64, device=self.device)
+            if n and g2.shape[1]:
+                self._launch_multi([(g2[i], p2[i]) for i in range(n)], block.data_ptr(), c2, self._cm_ptr)
+        self._per_image.append(block)
+
+    def per_image_matrices(self):
+        """(K,C,C) int64 ndarray: the confusion matrix of every image given to ``add_batch_per_image`` since the last
+        ``reset()``, in order (one D2H of K*C*C*8 bytes; synchronises)."""
+        self._fold()                       # surfaces the error flags of those launches
+        if not self._per_image:
+            return np.zeros((0, self.num_class, self.num_class), dtype=np.int64)
+        return torch.cat(self._per_image).cpu().numpy().reshape(-1, self.num_class, self.num_class)
+
+    def per_image_metrics(self):
+        """[(PA, MPA, MIoU, FWIoU), ...] per image, each value what the reference's ``Eval`` holding only that image
+        returns (``tools/analysis.py:177-183,212-214``): the same NumPy expressions on the float64 matrix."""
+        res = []
+        for m in self.per_image_matrices():
+            h = HostEval(self.num_class, m)
+            res.append((h.Pixel_Accuracy(), h.Mean_Pixel_Accuracy(), h.Mean_Intersection_over_Union(),
+                        h.Frequency_Weighted_Intersection_over_Union()))
+        return res
 
     def add_batch_logits(self, gt_image, logits):
         """Fused ``np.argmax(logits, axis=1)`` + ``add_batch`` (tools/train_source.py:457-459,492)."""
@@ -100,9 +201,9 @@ class Eval:
         gt = _to_device_labels(gt_image, self.device, self.num_class, True)
         lg = logits.contiguous()
         hw = lg.numel() // max(n * c, 1)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._flush_queue()
         _lib.check(_lib.load().msq_confusion_logits_f32(gt.data_ptr(), lg.data_ptr(), n, c, hw,
-                                                        self._dev.data_ptr(), stream))
+                                                        self._cm_ptr, _raw_stream(self._dev_index)))
         self._pending = True
 
     def add_batch_flip(self, gt_image, logits, logits_flipped):
@@ -119,25 +220,28 @@ class Eval:
             raise ValueError(f"logits have {c} classes, Eval was built with {self.num_class}")
         gt = _to_device_labels(gt_image, self.device, self.num_class, True)
         la, lb = logits.contiguous(), logits_flipped.contiguous()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._flush_queue()
         _lib.check(_lib.load().msq_confusion_flip_f32(gt.data_ptr(), la.data_ptr(), lb.data_ptr(), n, c, h, w,
-                                                      self._dev.data_ptr(), stream))
+                                                      self._cm_ptr, _raw_stream(self._dev_index)))
         self._pending = True
 
     def _fold(self):
         """device counts -> host float64 matrix (one small D2H, synchronises)."""
+        self._flush_queue()
         if not self._pending:
             return
         c2 = self.num_class ** 2
         host = self._dev.cpu().numpy()
         self._dev.zero_()
         self._pending = False
+        # the counts of every in-contract pixel are kept even when a batch tripped an error flag: the reference raises
+        # inside the offending add_batch and leaves what was accumulated before it intact (utils/eval.py:113-121)
+        self._host += host[:c2].reshape(self.num_class, self.num_class)
         flags = int(host[c2])
         if flags & 0xFFFFFFFF:
             raise ValueError("'list' argument must have no negative elements")      # numpy.bincount's message
         if flags >> 32:
             raise ValueError(f"cannot reshape array into shape ({self.num_class},{self.num_class})")
-        self._host += host[:c2].reshape(self.num_class, self.num_class)
 
     @property
     def confusion_matrix(self):
@@ -146,16 +250,23 @@ class Eval:
 
     @confusion_matrix.setter
     def confusion_matrix(self, value):
+        self._queue = []
         self._dev.zero_()
         self._pending = False
         self._host = np.asarray(value, dtype=np.float64)
 
     def device_counts(self):
+        self._flush_queue()
+        return self._device_counts()
+
+    def _device_counts(self):
         """(C,C) int64 CUDA tensor of the counts not yet folded to the host (for an
         NCCL all-reduce without a host round trip)."""
         return self._dev[:self.num_class ** 2].view(self.num_class, self.num_class)
 
     def reset(self):
+        self._queue = []
+        self._per_image = []
         self._dev.zero_()
         self._pending = False
         self._host = np.zeros((self.num_class,) * 2)
@@ -229,6 +340,20 @@ class Eval:
         for k in range(len(miou)):
             print('===>' + name_classes[k] + ':\t' + pct(mpa[k]) + '\t' + pct(miou[k]) + '\t' + pct(prec[k]) +
                   '\t' + pct(class_ratio[k]) + '\t' + pct(pred_ratio[k]))
+
+
+class HostEval(Eval):
+    """The metric methods of ``Eval`` on a given (C,C) matrix; no device, no accumulation (per-image metrics)."""
+
+    def __init__(self, num_class, matrix):          # noqa: super().__init__ needs a GPU and is not wanted here
+        self.num_class = num_class
+        self.ignore_index = None
+        self.synthia = True if num_class == 16 else False
+        self._host = np.asarray(matrix, dtype=np.float64)
+
+    @property
+    def confusion_matrix(self):
+        return self._host
 
 
 def fast_hist(gt, pred, num_class, device=None):

@@ -21,16 +21,23 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib
-from .loss import (_accum_buffer, _grad_out_ptr, _LossBase, _Outputs, _require_cuda_f32)
+from .loss import (_accum_buffer, _device_index, _grad_out_ptr, _LossBase, _new_out, _Outputs, _raw_stream, _require_cuda_f32)
 
 
 class _GuidanceOutputs(_Outputs):
-    def __init__(self, buf, n, c):
-        super().__init__(buf, n, c)
-        lay = _lib.state_layout(n, c)
-        self.loss2 = buf[lay.loss2_off:lay.loss2_off + 4].view(torch.float32).reshape(())
-        self.nvalid = buf[lay.nvalid_out_off:lay.nvalid_out_off + 8].view(torch.int64).reshape(())
-        self.ce_sum = buf[lay.ce_out_off:lay.ce_out_off + 8].view(torch.float64).reshape(())
+    __slots__ = ("loss2",)
+
+    def __init__(self, buf, n, c, lay=None):
+        super().__init__(buf, n, c, lay)
+        self.loss2 = buf[self.lay.loss2_off >> 2]
+
+    @property
+    def nvalid(self):
+        return self._view(self.lay.nvalid_out_off, 8, torch.int64).reshape(())
+
+    @property
+    def ce_sum(self):
+        return self._view(self.lay.ce_out_off, 8, torch.float64).reshape(())
 
 
 class _MultiLoss(torch.autograd.Function):
@@ -42,9 +49,9 @@ class _MultiLoss(torch.autograd.Function):
         lib = _lib.load()
         lay = _lib.state_layout(n, c)
         accum, stream = _accum_buffer(lo1.device, lay.accum_bytes)
-        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo1.device)
+        out = _new_out(lay, lo1.device)
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        nbytes = lib.msq_fused_aux_bytes(n, H, W)
+        nbytes = 16 * n * H * W                     # msq_fused_aux_bytes
         aux1 = torch.empty(nbytes, dtype=torch.uint8, device=lo1.device) if need1 else None
         aux2 = torch.empty(nbytes, dtype=torch.uint8, device=lo1.device) if need2 else None
         g1 = torch.empty_like(lo1) if need1 else None
@@ -54,7 +61,7 @@ class _MultiLoss(torch.autograd.Function):
         _lib.check(lib.msq_multi_fwd(mode, lo1.data_ptr(), lo2.data_ptr(), n, c, h, w, H, W, float(ratio),
                                      float(threshold), int(n_norm), accum.data_ptr(), out.data_ptr(), ptr(aux1), ptr(aux2),
                                      ptr(g1), ptr(g2), ptr(label2), stream))
-        o = _GuidanceOutputs(out, n, c)
+        o = _GuidanceOutputs(out, n, c, lay)
         loss2 = o.loss2
         if group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             # images sharded over ranks: CrossEntropyLoss averages over the valid pixels of the WHOLE
@@ -81,7 +88,7 @@ class _MultiLoss(torch.autograd.Function):
         mode, H, W, n_norm = ctx.cfg
         n, c, h, w = lo1.shape
         lib = _lib.load()
-        stream = torch.cuda.current_stream(lo1.device).cuda_stream
+        stream = _raw_stream(_device_index(lo1.device))
         r1 = r2 = None
         if ctx.needs_input_grad[0]:
             if g1 is None:

@@ -38,16 +38,28 @@ _accum_cache = {}
 #: fused mode: let the forward write the 16 B/pixel statistics cache for the backward
 USE_STATS_CACHE = True
 
+try:                                        # raw cudaStream_t of the current stream without building a torch.cuda.Stream
+    _raw_stream = torch._C._cuda_getCurrentRawStream          # (torch.cuda.current_stream() costs ~12 us per call)
+except AttributeError:                      # pragma: no cover
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+
+def _device_index(device):
+    idx = device.index
+    return idx if idx is not None else torch.cuda.current_device()
+
 
 def _accum_buffer(device, nbytes):
     """Zero-initialised, self-cleaning accumulator buffer, one per (device, stream)."""
-    stream = torch.cuda.current_stream(device)
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    idx = _device_index(device)
+    stream = _raw_stream(idx)
+    key = (idx, stream)
     buf = _accum_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=device)
         _accum_cache[key] = buf
-    return buf, stream.cuda_stream
+    return buf, stream
 
 
 def reset_workspaces():
@@ -78,16 +90,38 @@ def _prep_label(label, device, shape, name):
 
 
 class _Outputs:
-    """Views into the per-call output buffer of a forward."""
+    """The per-call output buffer of a forward (``msq_state_layout``: every member is 4-byte aligned, so the buffer
+    is allocated as float32 words).  Only ``loss`` is materialised eagerly (one indexing op); the other views are
+    built when somebody reads them -- a training step reads none."""
+    __slots__ = ("buf", "n", "c", "lay", "loss")
 
-    def __init__(self, buf, n, c):
-        lay = _lib.state_layout(n, c)
-        self.buf = buf
-        self.loss = buf[lay.loss_off:lay.loss_off + 4].view(torch.float32).reshape(())
-        self.weights = buf[lay.weights_off:lay.weights_off + 4 * n * c].view(torch.float32).view(n, c)
-        self.hist = buf[lay.hist_out_off:lay.hist_out_off + 4 * n * c].view(torch.int32).view(n, c)
-        self.sum_q = buf[lay.sum_out_off:lay.sum_out_off + 8 * n].view(torch.float64)
-        self.stats = buf[lay.stats_off:lay.stats_off + 8 * (1 + c)].view(torch.float64)
+    def __init__(self, buf, n, c, lay=None):
+        self.buf, self.n, self.c = buf, n, c
+        self.lay = lay if lay is not None else _lib.state_layout(n, c)
+        self.loss = buf[self.lay.loss_off >> 2]
+
+    def _view(self, off, nbytes, dtype):
+        return self.buf[off >> 2:(off + nbytes) >> 2].view(dtype)
+
+    @property
+    def weights(self):
+        return self._view(self.lay.weights_off, 4 * self.n * self.c, torch.float32).view(self.n, self.c)
+
+    @property
+    def hist(self):
+        return self._view(self.lay.hist_out_off, 4 * self.n * self.c, torch.int32).view(self.n, self.c)
+
+    @property
+    def sum_q(self):
+        return self._view(self.lay.sum_out_off, 8 * self.n, torch.float64)
+
+    @property
+    def stats(self):
+        return self._view(self.lay.stats_off, 8 * (1 + self.c), torch.float64)
+
+
+def _new_out(lay, device):
+    return torch.empty(lay.out_bytes >> 2, dtype=torch.float32, device=device)
 
 
 def _grad_out_ptr(grad_out, device):
@@ -106,11 +140,11 @@ class _ProbLoss(torch.autograd.Function):
         prob_c = prob.contiguous()
         lay = _lib.state_layout(n, c)
         accum, stream = _accum_buffer(prob.device, lay.accum_bytes)
-        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=prob.device)
+        out = _new_out(lay, prob.device)
         _lib.check(_lib.load().msq_prob_fwd(
             mode, prob_c.data_ptr(), n, c, h * w, label.data_ptr() if label is not None else None,
             float(ratio), int(ignore_index), int(n_norm), accum.data_ptr(), out.data_ptr(), stream))
-        o = _Outputs(out, n, c)
+        o = _Outputs(out, n, c, lay)
         sink.append(o)
         ctx.save_for_backward(prob_c)
         ctx.out = out
@@ -126,7 +160,7 @@ class _ProbLoss(torch.autograd.Function):
         n, c, h, w = prob.shape
         go = _grad_out_ptr(grad_out, prob.device)
         grad = torch.empty_like(prob)
-        stream = torch.cuda.current_stream(prob.device).cuda_stream
+        stream = _raw_stream(_device_index(prob.device))
         _lib.check(_lib.load().msq_prob_bwd(
             mode, prob.data_ptr(), n, c, h * w, int(ignore_index), int(n_norm), ctx.out.data_ptr(),
             go.data_ptr(), grad.data_ptr(), stream))
@@ -141,21 +175,24 @@ class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, label, out_size, mode, num_class, ratio, n_norm, sink):
         n, c, h, w = logits.shape
-        H, W = int(out_size[0]), int(out_size[1])
+        H, W = out_size
         lo = logits.contiguous()
-        lib = _lib.load()
         lay = _lib.state_layout(n, c)
-        accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
-        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
+        dev = lo.device
+        accum, stream = _accum_buffer(dev, lay.accum_bytes)
+        out = _new_out(lay, dev)
         aux = grad = None
+        aux_p = grad_p = None
         if ctx.needs_input_grad[0] and USE_STATS_CACHE:      # (grad mode is always off inside forward)
-            aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device=lo.device)
+            aux = torch.empty(16 * n * H * W, dtype=torch.uint8, device=dev)      # msq_fused_aux_bytes
             grad = torch.empty_like(lo)
-        _lib.check(lib.msq_fused_fwd(
+            aux_p, grad_p = aux.data_ptr(), grad.data_ptr()
+        rc = _lib.load().msq_fused_fwd(
             mode, lo.data_ptr(), n, c, h, w, H, W, label.data_ptr() if label is not None else None,
-            float(ratio), int(n_norm), accum.data_ptr(), out.data_ptr(),
-            aux.data_ptr() if aux is not None else None, grad.data_ptr() if grad is not None else None, stream))
-        o = _Outputs(out, n, c)
+            ratio, n_norm, accum.data_ptr(), out.data_ptr(), aux_p, grad_p, stream)
+        if rc:
+            _lib.check(rc)
+        o = _Outputs(out, n, c, lay)
         sink.append(o)
         ctx.save_for_backward(lo)
         ctx.out, ctx.aux, ctx.grad = out, aux, grad
@@ -174,10 +211,13 @@ class _FusedLoss(torch.autograd.Function):
         ctx.grad = None                       # the pre-zeroed buffer is good for one backward only
         if grad is None:
             grad, zeroed = torch.empty_like(lo), 0
-        stream = torch.cuda.current_stream(lo.device).cuda_stream
-        _lib.check(_lib.load().msq_fused_bwd(
-            mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(),
-            ctx.aux.data_ptr() if ctx.aux is not None else None, go.data_ptr(), grad.data_ptr(), zeroed, stream))
+        aux = ctx.aux
+        rc = _lib.load().msq_fused_bwd(
+            mode, lo.data_ptr(), n, c, h, w, H, W, n_norm, ctx.out.data_ptr(),
+            aux.data_ptr() if aux is not None else None, go.data_ptr(), grad.data_ptr(), zeroed,
+            _raw_stream(_device_index(lo.device)))
+        if rc:
+            _lib.check(rc)
         return (grad,) + (None,) * 7
 
 
@@ -191,11 +231,32 @@ class _LossBase(nn.Module):
         #: normaliser N of utils/loss.py:100 when the batch is sharded by image over
         #: ranks: set to the GLOBAL batch size (0 = this call's own N)
         self.global_batch = 0
-        #: device tensors of the most recent forward (no host sync to produce them)
-        self.last_hist = None        # (N,C) int32 per-image argmax/label histogram (IW)
-        self.last_weights = None     # (N,C) float32 image-wise class weights (IW)
-        self.last_sum_q = None       # (N,)  float64 per-image sum over pixels of sum_c p_c^2
-        self.last_stats = None       # (1+C,) float64 [loss, class histogram summed over images]: all-reduce me
+        self.__dict__["_last"] = None      # outputs of the most recent forward (plain attribute: nn.Module.__setattr__ costs 5 us)
+
+    # device tensors of the most recent forward (no host sync to produce them; views are built on access)
+    @property
+    def last_hist(self):
+        """(N,C) int32 per-image argmax/label histogram (IW)"""
+        o = self.__dict__["_last"]
+        return None if o is None else o.hist
+
+    @property
+    def last_weights(self):
+        """(N,C) float32 image-wise class weights (IW)"""
+        o = self.__dict__["_last"]
+        return None if o is None else o.weights
+
+    @property
+    def last_sum_q(self):
+        """(N,) float64 per-image sum over pixels of sum_c p_c^2"""
+        o = self.__dict__["_last"]
+        return None if o is None else o.sum_q
+
+    @property
+    def last_stats(self):
+        """(1+C,) float64 [loss, class histogram summed over images]: the vector to all-reduce over ranks"""
+        o = self.__dict__["_last"]
+        return None if o is None else o.stats
 
     def _check_classes(self, c):
         if c != self.num_class:
@@ -204,8 +265,7 @@ class _LossBase(nn.Module):
             raise RuntimeError(f"num_class={c} exceeds the kernels' limit of {_lib.MAX_CLASSES}")
 
     def _publish(self, sink):
-        o = sink[0]
-        self.last_hist, self.last_weights, self.last_sum_q, self.last_stats = o.hist, o.weights, o.sum_q, o.stats
+        self.__dict__["_last"] = sink[0]
 
     def _run(self, pred, prob, label, out_size, ratio):
         sink = []
@@ -220,8 +280,8 @@ class _LossBase(nn.Module):
                 raise RuntimeError("fused mode cannot honour an ignore_index inside [0,1]; use the strict mode")
             n = pred.shape[0]
             lab = _prep_label(label, pred.device, (n, int(out_size[0]), int(out_size[1])), "label")
-            loss = _FusedLoss.apply(pred, lab, tuple(out_size), self._mode, self.num_class, ratio,
-                                    self.global_batch, sink)
+            loss = _FusedLoss.apply(pred, lab, (int(out_size[0]), int(out_size[1])), self._mode, self.num_class,
+                                    float(ratio), int(self.global_batch), sink)
         else:
             _require_cuda_f32(prob, "prob")
             self._check_classes(prob.shape[1])
@@ -281,13 +341,13 @@ class _EntropyLoss(torch.autograd.Function):
         lib = _lib.load()
         lay = _lib.state_layout(n, c)
         accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
-        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
+        out = _new_out(lay, lo.device)
         need = ctx.needs_input_grad[0]
-        aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device=lo.device)
+        aux = torch.empty(16 * n * H * W, dtype=torch.uint8, device=lo.device)
         grad = torch.empty_like(lo) if need else None
         _lib.check(lib.msq_entropy_fwd(mode, lo.data_ptr(), n, c, h, w, H, W, float(ratio), int(n_norm), accum.data_ptr(),
                                        out.data_ptr(), aux.data_ptr(), grad.data_ptr() if need else None, stream))
-        o = _Outputs(out, n, c)
+        o = _Outputs(out, n, c, lay)
         sink.append(o)
         ctx.save_for_backward(lo)
         ctx.out, ctx.aux, ctx.grad = out, aux, grad
@@ -306,10 +366,47 @@ class _EntropyLoss(torch.autograd.Function):
         ctx.grad = None
         if grad is None:
             grad, zeroed = torch.empty_like(lo), 0
-        stream = torch.cuda.current_stream(lo.device).cuda_stream
+        stream = _raw_stream(_device_index(lo.device))
         _lib.check(_lib.load().msq_entropy_bwd(mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(),
                                                ctx.aux.data_ptr(), go.data_ptr(), grad.data_ptr(), zeroed, stream))
         return (grad,) + (None,) * 5
+
+
+class _SoftCE(torch.autograd.Function):
+    """Strict MinEnt: full-resolution ``inputs`` and an arbitrary ``target`` (``msq_softce_fwd`` / ``msq_softce_bwd``),
+    gradients for both (the trainers' target is ``softmax(inputs)``, attached to the graph)."""
+
+    @staticmethod
+    def forward(ctx, inputs, target, mode, ratio, ignore_index, n_norm, sink):
+        n, c, h, w = inputs.shape
+        z, t = inputs.contiguous(), target.contiguous()
+        lay = _lib.state_layout(n, c)
+        accum, stream = _accum_buffer(z.device, lay.accum_bytes)
+        out = _new_out(lay, z.device)
+        _lib.check(_lib.load().msq_softce_fwd(mode, z.data_ptr(), t.data_ptr(), n, c, h * w, float(ratio), int(ignore_index),
+                                              int(n_norm), accum.data_ptr(), out.data_ptr(), stream))
+        o = _Outputs(out, n, c, lay)
+        sink.append(o)
+        ctx.save_for_backward(z, t)
+        ctx.out = out
+        ctx.cfg = (mode, ignore_index, n_norm)
+        return o.loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        need_z, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_z or need_t):
+            return (None,) * 7
+        z, t = ctx.saved_tensors
+        mode, ignore_index, n_norm = ctx.cfg
+        n, c, h, w = z.shape
+        go = _grad_out_ptr(grad_out, z.device)
+        gz = torch.empty_like(z)
+        gt = torch.empty_like(t) if need_t else None
+        _lib.check(_lib.load().msq_softce_bwd(mode, z.data_ptr(), t.data_ptr(), n, c, h * w, int(ignore_index), int(n_norm),
+                                              ctx.out.data_ptr(), go.data_ptr(), gz.data_ptr(),
+                                              gt.data_ptr() if need_t else None, _raw_stream(_device_index(z.device))))
+        return (gz if need_z else None, gt) + (None,) * 5
 
 
 class _EntropyBase(_LossBase):
@@ -320,24 +417,29 @@ class _EntropyBase(_LossBase):
             raise RuntimeError(f"{c} classes exceed the kernels' limit of {_lib.MAX_CLASSES}")
         if self.num_class is not None:
             self._check_classes(c)
+        sink = []
         if target is not None:
-            # strict call, as the trainers make it (tools/solve_gta5.py:188-190,199): target IS softmax(inputs),
-            # attached to the graph.  It is not read: the kernels recompute it, and the gradient returned for
-            # `inputs` is the total derivative through both arguments.
+            # strict call (utils/loss.py:23-35, 46-67): ANY target distribution is honoured, read from memory, and both
+            # arguments receive their gradient (the trainers pass target = softmax(inputs) attached to the graph,
+            # tools/solve_gta5.py:188-190,199: autograd then adds the two paths up)
             assert inputs.size() == target.size()                      # utils/loss.py:29,52
             if out_size is not None and tuple(out_size) != tuple(inputs.shape[2:]):
                 raise RuntimeError("with a target tensor, inputs must already be at the target's resolution")
-            out_size = tuple(inputs.shape[2:])
-        elif out_size is None:
+            _require_cuda_f32(target, "target")
+            if target.device != inputs.device:
+                raise RuntimeError("inputs and target must be on the same device")
+            loss = _SoftCE.apply(inputs, target, self._mode, ratio, self.ignore_index, self.global_batch, sink)
+            self._publish(sink)
+            return loss
+        if out_size is None:
             raise RuntimeError("fused mode needs out_size=(H, W): forward(head_logits, out_size=...)")
-        sink = []
         loss = _EntropyLoss.apply(inputs, tuple(out_size), self._mode, ratio, self.global_batch, sink)
         self._publish(sink)
         return loss
 
 
 class softCrossEntropy(_EntropyBase):
-    """``mean(-log_softmax(inputs) * target)`` with ``target = softmax(inputs)`` (MinEnt,
+    """``mean((-log_softmax(inputs) * target)[target != ignore_index])`` (MinEnt when ``target = softmax(inputs)``,
     ``utils/loss.py:17-35``; selected by ``--target_mode entropy``, ``tools/solve_gta5.py:150-151``)."""
     _mode = _lib.MODE_MAXSQUARE
 
@@ -347,7 +449,8 @@ class softCrossEntropy(_EntropyBase):
     def forward(self, inputs, target=None, out_size=None):
         """
         :param inputs: predictions (N, C, H, W); in fused mode the low-resolution head logits (N, C, h, w)
-        :param target: target distribution (N, C, H, W) -- must be softmax(inputs), as every trainer passes it
+        :param target: target distribution (N, C, H, W): any values (the trainers pass softmax(inputs)); omit it for the
+                       fused mode, which computes softmax(up(inputs)) itself
         :param out_size: (H, W) label resolution, fused mode only
         :return: loss
         """
@@ -366,7 +469,7 @@ class IWsoftCrossEntropy(_EntropyBase):
     def forward(self, inputs, target=None, out_size=None):
         """
         :param inputs: predictions (N, C, H, W); in fused mode the low-resolution head logits (N, C, h, w)
-        :param target: target distribution (N, C, H, W) -- must be softmax(inputs)
+        :param target: target distribution (N, C, H, W): any values; omit it for the fused mode
         :param out_size: (H, W) label resolution, fused mode only
         :return: loss with image-wise weighting factor
         """

@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import _lib
 from .guidance import _GuidanceOutputs
-from .loss import _accum_buffer, _grad_out_ptr, _prep_label, _require_cuda_f32
+from .loss import _accum_buffer, _device_index, _grad_out_ptr, _new_out, _prep_label, _raw_stream, _require_cuda_f32
 
 
 class _SourceCE(torch.autograd.Function):
@@ -34,9 +34,9 @@ class _SourceCE(torch.autograd.Function):
         lib = _lib.load()
         lay = _lib.state_layout(n, c)
         accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
-        out = torch.empty(lay.out_bytes, dtype=torch.uint8, device=lo.device)
+        out = _new_out(lay, lo.device)
         need = ctx.needs_input_grad[0]
-        aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device=lo.device) if need else None
+        aux = torch.empty(16 * n * H * W, dtype=torch.uint8, device=lo.device) if need else None
         grad = torch.empty_like(lo) if need else None
         cm_ptr = None
         if evaluator is not None:
@@ -44,7 +44,7 @@ class _SourceCE(torch.autograd.Function):
             evaluator._pending = True
         _lib.check(lib.msq_source_ce_fwd(lo.data_ptr(), target.data_ptr(), n, c, h, w, H, W, accum.data_ptr(), out.data_ptr(),
                                          aux.data_ptr() if need else None, grad.data_ptr() if need else None, cm_ptr, stream))
-        o = _GuidanceOutputs(out, n, c)
+        o = _GuidanceOutputs(out, n, c, lay)
         loss = o.loss2
         if group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             # images sharded over ranks: the mean is over the valid pixels of the WHOLE batch
@@ -71,7 +71,7 @@ class _SourceCE(torch.autograd.Function):
         H, W = ctx.cfg
         n, c, h, w = lo.shape
         go = _grad_out_ptr(grad_out, lo.device)
-        stream = torch.cuda.current_stream(lo.device).cuda_stream
+        stream = _raw_stream(_device_index(lo.device))
         _lib.check(_lib.load().msq_guidance_bwd(lo.data_ptr(), n, c, h, w, H, W, out.data_ptr(), aux.data_ptr(), go.data_ptr(),
                                                 grad.data_ptr(), 1, stream))
         return (grad,) + (None,) * 5

@@ -92,14 +92,30 @@ def _worker_box(rank, world, port, q):
         outs = [torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda") for _ in range(K)]     # one per step in flight
         aux = torch.empty(lib.msq_fused_aux_bytes(N, H, W), dtype=torch.uint8, device="cuda")
         grad = torch.empty_like(los[0])
+        red = torch.zeros(K, 1 + C, dtype=torch.float64, device="cuda")
+        one = outs[0]                      # ONE `out` reused by every step: the communicator keeps no pointer into it
+        fetched = -1
         for i in range(K):
             _lib.check(lib.msq_fused_fwd_bwd(_lib.MODE_IW, los[i].data_ptr(), N, C, h, w, H, W, 0.2, N * world, accum.data_ptr(),
-                                             outs[i].data_ptr(), aux.data_ptr(), None, 0.1, grad.data_ptr(), comm._h, 0, stream))
+                                             one.data_ptr(), aux.data_ptr(), None, 0.1, grad.data_ptr(), comm._h, 0, stream))
             if i in flush_at:
                 comm.join()
+                for j in range(fetched + 1, i + 1):
+                    comm.result(1 + C, lag=i - j, out=red[j])
+                fetched = i
+            elif not comm.peer_memory:                        # NCCL: the fetch waits (on the stream) for the step's collective
+                comm.result(1 + C, lag=0, out=red[i])
+                fetched = i
+            elif i - 2 > fetched:                             # mailboxes: vector i-2 exists once step i has been enqueued
+                comm.result(1 + C, lag=2, out=red[i - 2])
+                fetched = i - 2
         comm.join()
+        for j in range(fetched + 1, K):
+            comm.result(1 + C, lag=K - 1 - j, out=red[j])
         torch.cuda.synchronize()
-        return np.stack([o[lay.stats_off:lay.stats_off + 8 * (1 + C)].view(torch.float64).cpu().numpy() for o in outs])
+        local = one[lay.stats_off:lay.stats_off + 8 * (1 + C)].view(torch.float64).cpu().numpy()
+        assert local[1:].sum() == N * H * W                  # the caller's `out` keeps the rank-LOCAL statistics
+        return red.cpu().numpy()
 
     box, nccl = mdist.StatsComm(), mdist.StatsComm(peer_memory=False)
     got = [run(box, ()), run(box, (0, 1, 6)), run(box, (K - 2,))]        # the communicator is reused; flushes anywhere
