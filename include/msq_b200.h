@@ -48,6 +48,9 @@ typedef void* msq_stream_t;         /* cudaStream_t */
 
 int         msq_abi_version(void);
 const char* msq_error_string(int code);
+/* number of kernels this library has launched in this process so far (bench.py reports the count of its timed region;
+ * memsets and NCCL's own kernels are not counted) */
+unsigned long long msq_launch_count(void);
 
 /* ---------------------------------------------------------------------------
  * Loss buffers.  A forward call uses two device buffers (byte offsets from

@@ -15,7 +15,7 @@ MODE_MAXSQUARE = 0
 MODE_IW = 1
 
 #: every symbol include/msq_b200.h declares
-SYMBOLS = ("msq_abi_version", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
+SYMBOLS = ("msq_abi_version", "msq_launch_count", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
            "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_i64_multi", "msq_confusion_per_image_logits_f32", "msq_softce_fwd", "msq_softce_bwd", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
            "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_join", "msq_comm_destroy",
            "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_enable", "msq_comm_box_active", "msq_comm_box_errors", "msq_comm_box_timeout", "msq_comm_result",
@@ -51,6 +51,8 @@ def load():
         vp, i32, i64, dbl = c.c_void_p, c.c_int, c.c_int64, c.c_double
         lib.msq_abi_version.restype = i32
         lib.msq_abi_version.argtypes = []
+        lib.msq_launch_count.restype = c.c_ulonglong
+        lib.msq_launch_count.argtypes = []
         lib.msq_error_string.restype = c.c_char_p
         lib.msq_error_string.argtypes = [i32]
         lib.msq_state_layout_get.restype = i32

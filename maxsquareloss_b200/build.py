@@ -4,6 +4,8 @@
 
 nvcc cross-compiles without a GPU; the built library sits in
 ``maxsquareloss_b200/lib/`` (git-ignored, but it travels with the working tree).
+``libmsq_torch.so`` next to it is the PyTorch host binding (``csrc/torch_binding.cpp``, g++): C++ autograd nodes that
+call the C ABI of ``libmsq_b200.so``.
 """
 import os
 import shutil
@@ -30,6 +32,10 @@ def _nvcc():
     raise RuntimeError("nvcc not found: libmsq_b200.so cannot be built (there is no CPU fallback)")
 
 
+TORCH_LIB = os.path.join(LIBDIR, "libmsq_torch.so")
+TORCH_SRC = os.path.join(CSRC, "torch_binding.cpp")
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True
@@ -38,12 +44,42 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def torch_binding_is_stale():
+    if not os.path.exists(TORCH_LIB):
+        return True
+    t = os.path.getmtime(TORCH_LIB)
+    return any(os.path.getmtime(d) > t for d in (TORCH_SRC, HEADERS[-1]))
+
+
+def build_torch_binding(force=False):
+    """g++ the PyTorch host binding against this interpreter's torch headers and link it to libmsq_b200.so
+    (``$ORIGIN`` run path: the two libraries travel together).  Returns its path."""
+    if not force and not torch_binding_is_stale():
+        return TORCH_LIB
+    import torch
+    tdir = os.path.dirname(os.path.abspath(torch.__file__))
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    if not cxx:
+        raise RuntimeError("g++ not found: libmsq_torch.so cannot be built")
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           "-I" + os.path.join(tdir, "include"), "-I" + os.path.join(tdir, "include", "torch", "csrc", "api", "include"),
+           "-I" + cuda_inc, TORCH_SRC, "-o", TORCH_LIB + ".tmp", "-L" + os.path.join(tdir, "lib"),
+           "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-L" + LIBDIR, "-lmsq_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr[-4000:])
+    os.replace(TORCH_LIB + ".tmp", TORCH_LIB)
+    return TORCH_LIB
+
+
 def build(force=False, verbose=False, defines=(), out=None):
     """Compile every CUDA source (one nvcc per file, in parallel) and link one shared library.
     Returns its path.  ``defines``/``out`` build an experimental variant next to the default library."""
     from concurrent.futures import ThreadPoolExecutor
     out = out or LIB
     if not force and not defines and not is_stale():
+        build_torch_binding()
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj" + ("_" + "_".join(defines).replace("=", "-") if defines else ""))
@@ -77,6 +113,8 @@ def build(force=False, verbose=False, defines=(), out=None):
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     os.replace(out + ".tmp", out)
+    if out == LIB:
+        build_torch_binding(force=True)
     return out
 
 

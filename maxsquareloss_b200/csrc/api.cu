@@ -43,7 +43,11 @@ int launch_finalize(const State& st, int mode, int n, int C, float r32, float om
 
 }  // namespace msq
 
+namespace msq { unsigned long long g_launches = 0ull; }
+
 extern "C" int msq_abi_version(void) { return MSQ_ABI_VERSION; }
+
+extern "C" unsigned long long msq_launch_count(void) { return __atomic_load_n(&msq::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* msq_error_string(int code) {
     switch (code) {

@@ -177,6 +177,7 @@ extern "C" int msq_comm_join(msq_comm* c, int lag, msq_stream_t stream) {
         c->pushed = K;
         c->reduced = K;
         MSQ_CHECK_LAUNCH();
+        msq::count_launch();
     }
     if (c->issued > (unsigned long long)lag) {
         const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, c->done[(c->issued - 1 - lag) % kRing], 0);

@@ -399,6 +399,9 @@ int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int 
 }  // namespace msq
 
 namespace msq {
+// every kernel this library launches is counted (msq_launch_count: bench.py reports the count of its timed region)
+extern unsigned long long g_launches;
+inline void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 // launch with the programmatic-stream-serialisation attribute (see pdl_wait / pdl_trigger)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -413,7 +416,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e == cudaSuccess) count_launch();
+    return e;
 }
 }  // namespace msq
 

@@ -278,10 +278,15 @@ confusion_multi_kernel(const ConfJobs jobs, int C, unsigned long long* __restric
         const int64_t* __restrict__ gt = jobs.gt[j];
         const int64_t* __restrict__ pr = jobs.pred[j];
         const long long npix = jobs.npix[j];
-        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        // every lane of a warp runs the same number of iterations: add_four votes across the whole warp
+        for (long long base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
+            const long long i = base + (threadIdx.x & 31u);
             long long g[4], p[4];
             int b[4];
-            if (VEC && 4 * i + 3 < npix) {
+            if (i >= hi) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { g[q] = -1; p[q] = 0; }
+            } else if (VEC && 4 * i + 3 < npix) {
                 const longlong2 ga = ldg_stream_l2(gt + 4 * i), gb = ldg_stream_l2(gt + 4 * i + 2);
                 const longlong2 pa = ldg_stream_l2(pr + 4 * i), pb = ldg_stream_l2(pr + 4 * i + 2);
                 g[0] = ga.x; g[1] = ga.y; g[2] = gb.x; g[3] = gb.y;

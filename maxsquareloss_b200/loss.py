@@ -31,7 +31,7 @@ Differences from the reference, all deliberate:
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, _torch_ops
 
 _accum_cache = {}
 
@@ -131,96 +131,6 @@ def _grad_out_ptr(grad_out, device):
     return g.contiguous()
 
 
-class _ProbLoss(torch.autograd.Function):
-    """Strict drop-in: full-resolution probabilities (kernels K3/K4)."""
-
-    @staticmethod
-    def forward(ctx, prob, label, mode, num_class, ratio, ignore_index, n_norm, sink):
-        n, c, h, w = prob.shape
-        prob_c = prob.contiguous()
-        lay = _lib.state_layout(n, c)
-        accum, stream = _accum_buffer(prob.device, lay.accum_bytes)
-        out = _new_out(lay, prob.device)
-        _lib.check(_lib.load().msq_prob_fwd(
-            mode, prob_c.data_ptr(), n, c, h * w, label.data_ptr() if label is not None else None,
-            float(ratio), int(ignore_index), int(n_norm), accum.data_ptr(), out.data_ptr(), stream))
-        o = _Outputs(out, n, c, lay)
-        sink.append(o)
-        ctx.save_for_backward(prob_c)
-        ctx.out = out
-        ctx.cfg = (mode, ignore_index, n_norm)
-        return o.loss
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        if not ctx.needs_input_grad[0]:
-            return (None,) * 8
-        (prob,) = ctx.saved_tensors
-        mode, ignore_index, n_norm = ctx.cfg
-        n, c, h, w = prob.shape
-        go = _grad_out_ptr(grad_out, prob.device)
-        grad = torch.empty_like(prob)
-        stream = _raw_stream(_device_index(prob.device))
-        _lib.check(_lib.load().msq_prob_bwd(
-            mode, prob.data_ptr(), n, c, h * w, int(ignore_index), int(n_norm), ctx.out.data_ptr(),
-            go.data_ptr(), grad.data_ptr(), stream))
-        return (grad,) + (None,) * 7
-
-
-class _FusedLoss(torch.autograd.Function):
-    """Fused: low-resolution head logits (kernels K1/K2).  When a gradient will be needed the
-    forward also zero-fills the future dL/dlogits buffer and writes the 16 B/pixel statistics
-    cache that lets the backward skip re-deriving max / argmax / normaliser."""
-
-    @staticmethod
-    def forward(ctx, logits, label, out_size, mode, num_class, ratio, n_norm, sink):
-        n, c, h, w = logits.shape
-        H, W = out_size
-        lo = logits.contiguous()
-        lay = _lib.state_layout(n, c)
-        dev = lo.device
-        accum, stream = _accum_buffer(dev, lay.accum_bytes)
-        out = _new_out(lay, dev)
-        aux = grad = None
-        aux_p = grad_p = None
-        if ctx.needs_input_grad[0] and USE_STATS_CACHE:      # (grad mode is always off inside forward)
-            aux = torch.empty(16 * n * H * W, dtype=torch.uint8, device=dev)      # msq_fused_aux_bytes
-            grad = torch.empty_like(lo)
-            aux_p, grad_p = aux.data_ptr(), grad.data_ptr()
-        rc = _lib.load().msq_fused_fwd(
-            mode, lo.data_ptr(), n, c, h, w, H, W, label.data_ptr() if label is not None else None,
-            ratio, n_norm, accum.data_ptr(), out.data_ptr(), aux_p, grad_p, stream)
-        if rc:
-            _lib.check(rc)
-        o = _Outputs(out, n, c, lay)
-        sink.append(o)
-        ctx.save_for_backward(lo)
-        ctx.out, ctx.aux, ctx.grad = out, aux, grad
-        ctx.cfg = (mode, H, W, n_norm)
-        return o.loss
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        if not ctx.needs_input_grad[0]:
-            return (None,) * 8
-        (lo,) = ctx.saved_tensors
-        mode, H, W, n_norm = ctx.cfg
-        n, c, h, w = lo.shape
-        go = _grad_out_ptr(grad_out, lo.device)
-        grad, zeroed = ctx.grad, 1
-        ctx.grad = None                       # the pre-zeroed buffer is good for one backward only
-        if grad is None:
-            grad, zeroed = torch.empty_like(lo), 0
-        aux = ctx.aux
-        rc = _lib.load().msq_fused_bwd(
-            mode, lo.data_ptr(), n, c, h, w, H, W, n_norm, ctx.out.data_ptr(),
-            aux.data_ptr() if aux is not None else None, go.data_ptr(), grad.data_ptr(), zeroed,
-            _raw_stream(_device_index(lo.device)))
-        if rc:
-            _lib.check(rc)
-        return (grad,) + (None,) * 7
-
-
 class _LossBase(nn.Module):
     _mode = None
 
@@ -234,28 +144,36 @@ class _LossBase(nn.Module):
         self.__dict__["_last"] = None      # outputs of the most recent forward (plain attribute: nn.Module.__setattr__ costs 5 us)
 
     # device tensors of the most recent forward (no host sync to produce them; views are built on access)
+    def _outputs(self):
+        o = self.__dict__["_last"]
+        if o is None or isinstance(o, _Outputs):
+            return o
+        o = _Outputs(*o)
+        self.__dict__["_last"] = o
+        return o
+
     @property
     def last_hist(self):
         """(N,C) int32 per-image argmax/label histogram (IW)"""
-        o = self.__dict__["_last"]
+        o = self._outputs()
         return None if o is None else o.hist
 
     @property
     def last_weights(self):
         """(N,C) float32 image-wise class weights (IW)"""
-        o = self.__dict__["_last"]
+        o = self._outputs()
         return None if o is None else o.weights
 
     @property
     def last_sum_q(self):
         """(N,) float64 per-image sum over pixels of sum_c p_c^2"""
-        o = self.__dict__["_last"]
+        o = self._outputs()
         return None if o is None else o.sum_q
 
     @property
     def last_stats(self):
         """(1+C,) float64 [loss, class histogram summed over images]: the vector to all-reduce over ranks"""
-        o = self.__dict__["_last"]
+        o = self._outputs()
         return None if o is None else o.stats
 
     def _check_classes(self, c):
@@ -267,29 +185,38 @@ class _LossBase(nn.Module):
     def _publish(self, sink):
         self.__dict__["_last"] = sink[0]
 
-    def _run(self, pred, prob, label, out_size, ratio):
-        sink = []
+    def _run(self, pred, prob, label, out_size, ratio, kind=0):
+        """One forward through the C++ autograd node (``torch.ops.msq_b200.*``, csrc/torch_binding.cpp): the checks that
+        need no Python (device, dtype, rank, label shape) are made there."""
+        ops = _torch_ops.load()
         if prob is None:
             if out_size is None:
                 raise RuntimeError("fused mode needs out_size=(H, W): forward(head_logits, out_size=...)")
-            _require_cuda_f32(pred, "head logits")
-            self._check_classes(pred.shape[1])
+            if not isinstance(pred, torch.Tensor):
+                raise RuntimeError("head logits must be a torch.Tensor")
+            c = pred.shape[1] if pred.dim() == 4 else -1
+            if c != self.num_class and c >= 0 and self.num_class is not None:
+                self._check_classes(c)
             # a softmax output never equals an ignore value outside [0,1], so the reference's masks
             # (utils/loss.py:85,117) are all-true and the fused kernels do not evaluate them
-            if 0.0 <= float(self.ignore_index) <= 1.0:
+            if 0.0 <= self.ignore_index <= 1.0:
                 raise RuntimeError("fused mode cannot honour an ignore_index inside [0,1]; use the strict mode")
+            H, W = int(out_size[0]), int(out_size[1])
+            if label is not None:
+                label = _prep_label(label, pred.device, (pred.shape[0], H, W), "label")
+            loss, out = ops.fused_loss(pred, label, H, W, self._mode, float(ratio), int(self.global_batch), kind, USE_STATS_CACHE)
             n = pred.shape[0]
-            lab = _prep_label(label, pred.device, (n, int(out_size[0]), int(out_size[1])), "label")
-            loss = _FusedLoss.apply(pred, lab, (int(out_size[0]), int(out_size[1])), self._mode, self.num_class,
-                                    float(ratio), int(self.global_batch), sink)
         else:
-            _require_cuda_f32(prob, "prob")
-            self._check_classes(prob.shape[1])
-            n, _, h, w = prob.shape
-            lab = _prep_label(label, prob.device, (n, h, w), "label")
-            loss = _ProbLoss.apply(prob, lab, self._mode, self.num_class, ratio, self.ignore_index,
-                                   self.global_batch, sink)
-        self._publish(sink)
+            if not isinstance(prob, torch.Tensor):
+                raise RuntimeError("prob must be a torch.Tensor")
+            c = prob.shape[1] if prob.dim() == 4 else -1
+            if c != self.num_class and c >= 0:
+                self._check_classes(c)
+            if label is not None:
+                label = _prep_label(label, prob.device, (prob.shape[0],) + tuple(prob.shape[2:]), "label")
+            loss, out = ops.prob_loss(prob, label, self._mode, float(ratio), int(self.ignore_index), int(self.global_batch))
+            n = prob.shape[0]
+        self.__dict__["_last"] = (out, n, c)
         return loss
 
 
@@ -328,48 +255,6 @@ class IW_MaxSquareloss(_LossBase):
         :return: maximum squares loss with image-wise weighting factor (0-dim CUDA tensor)
         """
         return self._run(pred, prob, label, out_size, self.ratio)
-
-
-class _EntropyLoss(torch.autograd.Function):
-    """MinEnt losses, fused from head logits (``msq_entropy_fwd`` / ``msq_entropy_bwd``)."""
-
-    @staticmethod
-    def forward(ctx, logits, out_size, mode, ratio, n_norm, sink):
-        n, c, h, w = logits.shape
-        H, W = int(out_size[0]), int(out_size[1])
-        lo = logits.contiguous()
-        lib = _lib.load()
-        lay = _lib.state_layout(n, c)
-        accum, stream = _accum_buffer(lo.device, lay.accum_bytes)
-        out = _new_out(lay, lo.device)
-        need = ctx.needs_input_grad[0]
-        aux = torch.empty(16 * n * H * W, dtype=torch.uint8, device=lo.device)
-        grad = torch.empty_like(lo) if need else None
-        _lib.check(lib.msq_entropy_fwd(mode, lo.data_ptr(), n, c, h, w, H, W, float(ratio), int(n_norm), accum.data_ptr(),
-                                       out.data_ptr(), aux.data_ptr(), grad.data_ptr() if need else None, stream))
-        o = _Outputs(out, n, c, lay)
-        sink.append(o)
-        ctx.save_for_backward(lo)
-        ctx.out, ctx.aux, ctx.grad = out, aux, grad
-        ctx.cfg = (mode, H, W, n_norm)
-        return o.loss
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        if not ctx.needs_input_grad[0]:
-            return (None,) * 6
-        (lo,) = ctx.saved_tensors
-        mode, H, W, n_norm = ctx.cfg
-        n, c, h, w = lo.shape
-        go = _grad_out_ptr(grad_out, lo.device)
-        grad, zeroed = ctx.grad, 1
-        ctx.grad = None
-        if grad is None:
-            grad, zeroed = torch.empty_like(lo), 0
-        stream = _raw_stream(_device_index(lo.device))
-        _lib.check(_lib.load().msq_entropy_bwd(mode, lo.data_ptr(), n, c, h, w, H, W, int(n_norm), ctx.out.data_ptr(),
-                                               ctx.aux.data_ptr(), go.data_ptr(), grad.data_ptr(), zeroed, stream))
-        return (grad,) + (None,) * 5
 
 
 class _SoftCE(torch.autograd.Function):
@@ -431,11 +316,7 @@ class _EntropyBase(_LossBase):
             loss = _SoftCE.apply(inputs, target, self._mode, ratio, self.ignore_index, self.global_batch, sink)
             self._publish(sink)
             return loss
-        if out_size is None:
-            raise RuntimeError("fused mode needs out_size=(H, W): forward(head_logits, out_size=...)")
-        loss = _EntropyLoss.apply(inputs, tuple(out_size), self._mode, ratio, self.global_batch, sink)
-        self._publish(sink)
-        return loss
+        return self._run(inputs, None, None, out_size, ratio, kind=1)        # MinEnt variant of the fused kernels
 
 
 class softCrossEntropy(_EntropyBase):

@@ -44,6 +44,19 @@ for sync in (False, True):
     tot = time.perf_counter() - t0
     print(f"sync={sync}: {tot / n * 1e6:.1f} us/step  " + "  ".join(f"{k} {v / n * 1e6:.1f}" for k, v in T.items()), flush=True)
 
+# PyTorch's own fixed cost for the same call pattern with a NATIVE one-kernel loss (x.sum()): what no binding can remove
+def floor_step(i):
+    x = dev_in.detach().requires_grad_(True)
+    (0.1 * x.sum()).backward()
+for i in range(200): floor_step(i)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for i in range(2000):
+    floor_step(i)
+    if i % 64 == 63: cur.synchronize()
+torch.cuda.synchronize()
+print(f"torch floor (x.sum() as the loss: detach + sum + lambda*loss + backward): {(time.perf_counter() - t0) / 2000 * 1e6:.1f} us/step", flush=True)
+
 pr = cProfile.Profile()
 pr.enable()
 for i in range(2000):

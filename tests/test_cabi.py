@@ -146,3 +146,24 @@ def test_peer_memory_mailbox_argument_checks(lib):
     assert lib.msq_comm_box_enable(None, 1) == -1
     v = ctypes.c_uint(7)
     assert lib.msq_comm_box_errors(None, ctypes.byref(v)) == -1
+
+
+def test_torch_binding_loads_and_has_no_cpu_fallback(lib):
+    """lib/libmsq_torch.so (the C++ autograd nodes over the C ABI) loads next to libmsq_b200.so, registers its two
+    operators and refuses CPU tensors; the nn.Modules go through it."""
+    import torch
+    import maxsquareloss_b200 as msq
+    from maxsquareloss_b200 import _torch_ops
+    ops = _torch_ops.load()
+    assert str(ops.fused_loss) == "msq_b200.fused_loss.default" and str(ops.prob_loss) == "msq_b200.prob_loss.default"
+    lo = torch.randn(1, 19, 4, 4, requires_grad=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.fused_loss(lo, None, 8, 8, 1, 0.2, 0, 0, True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.IW_MaxSquareloss(-1, 19, 0.2)(lo, out_size=(8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msq.MaxSquareloss(-1, 19)(None, torch.softmax(lo, 1))
+    with pytest.raises(ValueError):
+        msq.MaxSquareloss(-1, 16)(None, torch.softmax(lo, 1))
+    with pytest.raises(RuntimeError, match="out_size"):
+        msq.IW_MaxSquareloss(-1, 19, 0.2)(lo)
