@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Benchmark of the MaxSquare hot path on B200 (contract: see the task brief / DESIGN.md).
+"""Benchmark of the MaxSquare hot path on B200 (contract: see the task brief / DESIGN.md section 5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -10,13 +10,16 @@ one pass of the hot path over that batch: fused IW-MaxSquare forward (bilinear u
 softmax + per-image argmax histogram + image-wise weights + loss) and backward (dL/dlogits
 at 65x129).  Metric: Gpixel/s = label-resolution pixels / time.
 
-  value  device-resident inputs, kernels launched through the C ABI (ctypes)
-  e2e    the same step through the public Python API (IW_MaxSquareloss module +
-         autograd) with pinned HOST logits in and the loss + dL/dlogits back on the host
+  value  device-resident inputs, kernels launched through the C ABI (ctypes), CUDA-event timed
+  e2e    the same step through the REFERENCE'S API -- the IW_MaxSquareloss nn.Module + autograd, called as
+         tools/solve_gta5.py:199,217 call it -- with pinned HOST logits in and the loss + dL/dlogits back on the
+         host every step (e2e.c_abi_pipeline: the same through the C-ABI host pipeline, no PyTorch autograd)
 
-Weak scaling: every rank owns its own 2 images (sharding by image); for N > 1 each step
-also all-reduces the packed [loss, class histogram] vector (dist.StatsComm): over NVLink peer-memory mailboxes
-written by the step's own finalisation kernel, or -- where CUDA IPC is not available -- with one ncclAllReduce.
+Weak scaling: every rank owns its own 2 images (sharding by image); for N > 1 each step also exchanges the packed
+[loss, class histogram] vector (dist.StatsComm): over NVLink peer-memory mailboxes written by the step's own
+finalisation kernel, or -- where CUDA IPC is not available -- with one ncclAllReduce.  The N > 1 runs also carry
+the cfg-3 (multi-level guidance, batch 8 strong-sharded) and cfg-5 (crosscity step, 1 image per GPU) legs and the
+cross-rank parity checks (stats_check, cfg3.check, cfg5.check).
 
 ``--impl reference`` times the reference's algorithm on the host CPU (oracle/loss_port.py:
 F.interpolate -> softmax -> IW loss -> backward, all host threads).
@@ -44,6 +47,12 @@ POOL = 128                               # distinct input buffers: 128 x 1.27 MB
 PX_PER_STEP = N_IMG * HW_OUT[0] * HW_OUT[1]
 WORKLOAD = ("cfg2 GTA5->Cityscapes target shape: IW-MaxSquare fwd+bwd, batch 2/GPU, 19 classes, "
             "head logits 65x129 -> 512x1024, ratio 0.2")
+
+
+def shared_config(n_gpus):
+    """``config`` of the JSON line: the SAME dict from both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "images_per_gpu": N_IMG, "global_batch": N_IMG * n_gpus, "num_class": C,
+            "head_logits_hw": list(HW_LO), "label_hw": list(HW_OUT), "iw_ratio": RATIO, "lambda_target": LAMBDA_TARGET}
 
 
 def peaks():
@@ -166,7 +175,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "arm": "reference algorithm on host CPU (oracle port)"},
+            "config": shared_config(args.gpus),
+            "arm": "the reference's algorithm on the host CPU (oracle port of F.interpolate -> softmax -> IW_MaxSquareloss -> backward)",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -188,6 +198,90 @@ def time_loop(fn, iters, warm):
     return a.elapsed_time(b) / iters          # ms per call
 
 
+def max_over_ranks(x, dev, dist, world):
+    if world == 1:
+        return float(x)
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def api_e2e_leg(msq, crit, host_in, dev, steps, depth, sync_every_step, comm):
+    """The step through the reference's API, exactly as tools/solve_gta5.py:199,217 spell it -- ``loss = crit(...)``,
+    ``(lambda_target * loss).backward()`` -- around the host copies the contract asks for: every step copies that
+    step's head logits from pinned host memory (H2D) and copies the loss and dL/dlogits back to pinned host memory (D2H).
+    ``sync_every_step``: the host waits for the step's results before it issues the next one (a trainer that logs
+    ``loss.item()`` every iteration); otherwise it reads the results of step i-depth when it reuses that slot's buffers
+    (a trainer that logs with a lag).  Sharded runs also all-reduce the step's [loss | hist] vector (StatsComm).
+    Returns seconds per step (wall clock around ``steps`` steps, drained)."""
+    shape = (N_IMG, C) + tuple(HW_LO)
+    dev_in = [torch.empty(shape, device=dev) for _ in range(depth)]
+    host_grad = [torch.empty(shape).pin_memory() for _ in range(depth)]
+    host_loss = [torch.empty(()).pin_memory() for _ in range(depth)]
+    stats = [torch.zeros(1 + C, dtype=torch.float64, device=dev) for _ in range(depth)]
+    done = [torch.cuda.Event() for _ in range(depth)]
+    cur = torch.cuda.current_stream()
+    npool = len(host_in)
+    seen = [0.0]
+
+    def step(i):
+        k = i % depth
+        if i >= depth:
+            done[k].synchronize()                      # step i-depth is complete: its loss / gradient are on the host
+            seen[0] += float(host_loss[k])             # ... and the host reads them
+        dev_in[k].copy_(host_in[i % npool], non_blocking=True)                  # H2D
+        x = dev_in[k].detach().requires_grad_(True)
+        loss = crit(x, out_size=HW_OUT)
+        (LAMBDA_TARGET * loss).backward()
+        host_grad[k].copy_(x.grad, non_blocking=True)                           # D2H
+        host_loss[k].copy_(loss.detach(), non_blocking=True)
+        if comm is not None:
+            stats[k].copy_(crit.last_stats)
+            comm.allreduce(stats[k])
+            comm.join(lag=1)                           # the previous step's collective; this one overlaps the next step
+        done[k].record(cur)
+        if sync_every_step:
+            done[k].synchronize()
+
+    for i in range(max(3 * depth, 30)):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    if comm is not None:
+        comm.join()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps, float(host_loss[(steps - 1) % depth])
+
+
+def torch_floor(dev, host_in, steps):
+    """PyTorch's own fixed host cost for the same call pattern with a NATIVE one-kernel loss (``x.sum()``): detach +
+    loss + ``lambda * loss`` + ``.backward()`` + the same copies.  No binding of this library can go below it."""
+    shape = (N_IMG, C) + tuple(HW_LO)
+    dev_in = torch.empty(shape, device=dev)
+    host_grad, host_loss = torch.empty(shape).pin_memory(), torch.empty(()).pin_memory()
+    cur = torch.cuda.current_stream()
+
+    def step(i):
+        dev_in.copy_(host_in[i % len(host_in)], non_blocking=True)
+        x = dev_in.detach().requires_grad_(True)
+        loss = x.sum()
+        (LAMBDA_TARGET * loss).backward()
+        host_grad.copy_(x.grad, non_blocking=True)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        if i % 64 == 63:
+            cur.synchronize()
+    for i in range(64):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     import maxsquareloss_b200 as msq
@@ -199,7 +293,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the only collectives of this program carry 160 bytes: one NCCL CTA is plenty, and the one-wave kernels then
+        # the only collectives of this program carry <= 3 KB: one NCCL CTA is plenty, and the one-wave kernels then
         # lose fewer SM slots to it (8 GPUs: 183.8 -> 196.2 Gpix/s together with reserve_sms=2)
         os.environ.setdefault("NCCL_MAX_CTAS", "1")
         os.environ.setdefault("NCCL_MIN_CTAS", "1")
@@ -257,15 +351,13 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         # NCCL path: room for the NCCL kernel next to the one-wave grids; peer-memory mailboxes: no collective kernel at all
         _lib.tune("reserve_sms", int(os.environ.get("MSQ_RESERVE_SMS", "0" if comm.peer_memory else "2")))
-    stats_ptrs = [v.data_ptr() for v in stats_views]
     n_stats = 1 + C
-
     comm_h = comm._h if comm is not None else None
 
     def step(i):
         # ONE library call per step (C ABI msq_fused_fwd_bwd): fused forward, finalise, backward and -- when sharded --
-        # the statistics all-reduce (NCCL, side stream), forked AFTER the backward so that no stream operation sits
-        # between forward -> finalise -> backward (that would break their programmatic dependent launches)
+        # the statistics exchange (mailboxes inside the finalisation kernel, or ncclAllReduce forked AFTER the backward so
+        # that no stream operation sits between forward -> finalise -> backward)
         j = i % POOL
         rc = lib.msq_fused_fwd_bwd(MODE, lo_ptrs[j], N_IMG, C, h, w, H, W, RATIO, n_norm, acc_ptr, out_ptrs[j],
                                    aux_ptrs[i % AUX_POOL], go_ptr, 0.0, gr_ptrs[j], comm_h, COMM_LAG, stream)
@@ -273,7 +365,7 @@ def run_b200(args, rank, world, local_rank):
             _lib.check(rc)
 
     # ---- warm-up: at least W steps, and enough of them (~0.2 s) for the clocks to be up.  The count is FIXED, not
-    #      time-based: every rank must issue the same number of all-reduces
+    #      time-based: every rank must issue the same number of exchanges.  All of it is reported as `warmup`.
     warm_steps = warm if os.environ.get("MSQ_BENCH_MIN_WARM_S") == "0" else max(warm, 5000)      # "0": under ncu
     for i in range(warm_steps):
         step(i)
@@ -282,30 +374,6 @@ def run_b200(args, rank, world, local_rank):
     if comm is not None:
         comm.join(stream)
     torch.cuda.synchronize()
-
-    if os.environ.get("MSQ_BENCH_AB"):      # diagnostic: the timed loop under different clock-sampler settings
-        for tag, interval in (("none", None), ("2ms", 0.002), ("20ms", 0.02), ("none", None), ("2ms", 0.002)):
-            smp = ClockSampler(local_rank, interval) if interval else None
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            if smp:
-                smp.start()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(steps):
-                step(i)
-            if comm is not None:
-                comm.join(stream)
-            b.record()
-            torch.cuda.synchronize()
-            if smp:
-                smp.stop()
-            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            if rank == 0:
-                sys.stderr.write(f"[ab] sampler {tag}: {float(t.item()) / steps * 1e3:.2f} us/step\n")
 
     # ---- timed region: EXACTLY `steps` steps, barrier + synchronize on both sides, max over ranks
     sampler = ClockSampler(local_rank)
@@ -317,36 +385,62 @@ def run_b200(args, rank, world, local_rank):
     # the last warm-up steps run AFTER the barrier + synchronize, back to back with the timed ones: the first steps after
     # an idle stream carry the host's launch latency, the sampler thread's start-up and -- on 8 ranks -- tens of
     # milliseconds of skew between the ranks (measured: 48.8 us/step for the first 2000 steps after the barrier against
-    # 36.7 us/step for every later 2000, MSQ_BENCH_AB=1); they are warm-up, not steady state
-    REWARM = max(256, min(steps, 4000))        # as many again as are timed: whatever the transient is, it is over
+    # 36.7 us/step for every later 2000); they are warm-up, not steady state
+    REWARM = 0 if os.environ.get("MSQ_BENCH_MIN_WARM_S") == "0" else max(256, min(steps, 4000))
     for i in range(REWARM):
         step(steps - REWARM + i)
+    launches0 = int(lib.msq_launch_count())
     ev0.record()
     for i in range(steps):
         step(i)
     if comm is not None:
         comm.join(stream)
     ev1.record()
+    launches = int(lib.msq_launch_count()) - launches0          # counted by the library: every kernel it launched in there
     torch.cuda.synchronize()
     clocks = sampler.stop()
     if world > 1:
         dist.barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_rank = ev0.elapsed_time(ev1)
+    ms_total = max_over_ranks(ms_rank, dev, dist, world)
     ms_per_step = ms_total / steps
     value = world * PX_PER_STEP / (ms_per_step * 1e-3) / 1e9
+    rank_spread = None
+    if world > 1:
+        allms = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms_rank / steps * 1e3], device=dev, dtype=torch.float64))
+        rank_spread = {"us_per_step_by_rank": [round(float(t.item()), 3) for t in allms]}
+
+    # ---- cross-rank parity of the exchange (SCALE runs): the vector the mailboxes (or the library's ncclAllReduce)
+    #      produced for the LAST timed step against (a) torch.distributed's NCCL all-reduce of the ranks' local vectors and
+    #      (b) their sum in rank order: histogram bit-exact, loss <= 1e-6 relative
     stats_check = None
     if comm is not None:
-        # the all-reduced [loss | hist] of the last timed step: every pixel of every rank's images must be counted
-        last = stats_views[(steps - 1) % POOL]
-        hist_total = float(last[1:].sum().item())
+        local = stats_views[(steps - 1) % POOL].clone()
+        got = comm.result(n_stats, lag=0)
+        ref_nccl = local.clone()
+        dist.all_reduce(ref_nccl, op=dist.ReduceOp.SUM)
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        ref_sum = parts[0].clone()
+        for t_ in parts[1:]:
+            ref_sum += t_
+        torch.cuda.synchronize()
+        hist_total = float(got[1:].sum().item())
         err = comm.errors() if comm.peer_memory else 0
-        stats_check = {"hist_total": hist_total, "expected": float(world * PX_PER_STEP), "mailbox_errors": err,
-                       "ok": hist_total == float(world * PX_PER_STEP) and err == 0,
-                       "exchange": "nvlink peer-memory mailboxes" if comm.peer_memory else "ncclAllReduce"}
+        rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-300)          # noqa: E731
+        ok_local = (torch.equal(got[1:], ref_nccl[1:]) and torch.equal(got[1:], ref_sum[1:]) and
+                    rel(got[0], ref_nccl[0]) <= 1e-6 and rel(got[0], ref_sum[0]) <= 1e-6 and
+                    hist_total == float(world * PX_PER_STEP) and err == 0)
+        okt = torch.tensor([1 if ok_local else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        stats_check = {"exchange": "nvlink peer-memory mailboxes" if comm.peer_memory else "ncclAllReduce (library communicator)",
+                       "hist_bit_exact_vs_nccl_allreduce": bool(torch.equal(got[1:], ref_nccl[1:])),
+                       "hist_bit_exact_vs_rank_order_sum": bool(torch.equal(got[1:], ref_sum[1:])),
+                       "loss_rel_vs_nccl_allreduce": rel(got[0], ref_nccl[0]), "loss_rel_vs_rank_order_sum": rel(got[0], ref_sum[0]),
+                       "loss_bit_identical_to_rank_order_sum": bool(float(got[0]) == float(ref_sum[0])),
+                       "hist_total": hist_total, "expected_hist_total": float(world * PX_PER_STEP), "mailbox_errors": err,
+                       "loss_allreduced": float(got[0]), "ok": bool(int(okt.item()) == 1)}
 
     # ---- the same step in the "hot" regime: one buffer set every iteration (the 1.27 MB of logits and the 16.8 MB
     #      statistics cache then live in L2); reported next to the cold number above, never instead of it
@@ -354,20 +448,34 @@ def run_b200(args, rank, world, local_rank):
     if comm is not None:
         comm.join(stream)
         torch.cuda.synchronize()
-        t = torch.tensor([hot_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        hot_ms = float(t.item())
+    hot_ms = max_over_ranks(hot_ms, dev, dist, world)
 
-    # ---- e2e (headline): C-ABI host-buffer pipeline (maxsquareloss_b200.HostPipeline -> msq_pipe_submit):
-    #      every step copies its head logits from pinned HOST memory, runs fwd+bwd and copies the loss
-    #      and dL/dlogits back to the host; `depth` steps in flight so copies overlap kernels.
+    # ---- e2e (headline): the reference's API.  IW_MaxSquareloss nn.Module + autograd with host copies every step
     e2e_pool = min(POOL, 16)
     host_in = [lo_pool[i].cpu().pin_memory() for i in range(e2e_pool)]
+    crit = msq.IW_MaxSquareloss(-1, C, RATIO)
+    crit.global_batch = n_norm
+    API_DEPTH = 4
+    api_steps = max(20, min(steps, 1000))
+    if world > 1:
+        dist.barrier()
+    api_s, api_last_loss = api_e2e_leg(msq, crit, host_in, dev, api_steps, API_DEPTH, False, comm)
+    api_s = max_over_ranks(api_s, dev, dist, world)
+    if world > 1:
+        dist.barrier()
+    api_sync_s, _ = api_e2e_leg(msq, crit, host_in, dev, min(api_steps, 500), 1, True, comm)
+    api_sync_s = max_over_ranks(api_sync_s, dev, dist, world)
+    floor_s = max_over_ranks(torch_floor(dev, host_in, min(api_steps, 500)), dev, dist, world)
+    e2e_val = world * PX_PER_STEP / api_s / 1e9
+
+    # ---- the same through the C-ABI host-buffer pipeline (maxsquareloss_b200.HostPipeline -> msq_pipe_submit, three
+    #      streams, `depth` steps in flight): no PyTorch autograd; sharded runs use the global normaliser and the exchange
     depth = int(os.environ.get("MSQ_BENCH_DEPTH", "16"))         # a step is ~100 us of latency end to end (H2D, kernels, D2H)
-    pipe = msq.HostPipeline("iw", N_IMG, C, HW_LO, HW_OUT, ratio=RATIO, depth=depth)
+    pipe = msq.HostPipeline("iw", N_IMG, C, HW_LO, HW_OUT, ratio=RATIO, depth=depth, comm=comm,
+                            global_batch=n_norm if world > 1 else 0)
     h_grad = [torch.empty(N_IMG, C, *HW_LO).pin_memory() for _ in range(depth)]
     h_loss = [torch.empty(()).pin_memory() for _ in range(depth)]
-    e2e_steps = steps
+    pipe_steps = max(steps, 200)
 
     def pipe_run(nsteps):
         slots = []
@@ -378,156 +486,154 @@ def run_b200(args, rank, world, local_rank):
             slots.append(pipe.submit(host_in[i % e2e_pool], h_loss[j], h_grad[j], None, LAMBDA_TARGET))
         pipe.drain()
 
-    pipe_run(max(warm, 30))
+    pipe_run(max(warm, 64))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pipe_run(e2e_steps)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = world * PX_PER_STEP * e2e_steps / e2e_s / 1e9
-    last_loss = float(h_loss[(e2e_steps - 1) % depth].item())
+    pipe_run(pipe_steps)
+    pipe_s = max_over_ranks(time.perf_counter() - t0, dev, dist, world)
+    pipe_val = world * PX_PER_STEP * pipe_steps / pipe_s / 1e9
+    pipe_last_loss = float(h_loss[(pipe_steps - 1) % depth].item())
     pipe.close()
 
-    # ---- e2e through nn.Module + autograd, host sync every step (what a PyTorch trainer does)
-    crit = msq.IW_MaxSquareloss(-1, C, RATIO)
-    crit.global_batch = n_norm
-    host_grad = torch.empty(N_IMG, C, *HW_LO).pin_memory()
-    host_loss = torch.empty(()).pin_memory()
-    dev_in = torch.empty(N_IMG, C, *HW_LO, device=dev)
-    cur = torch.cuda.current_stream()
-
-    def ag_step(i):
-        dev_in.copy_(host_in[i % e2e_pool], non_blocking=True)                 # H2D
-        x = dev_in.detach().requires_grad_(True)
-        loss = crit(x, out_size=HW_OUT)
-        (LAMBDA_TARGET * loss).backward()
-        host_grad.copy_(x.grad, non_blocking=True)                              # D2H
-        host_loss.copy_(loss.detach(), non_blocking=True)
-        cur.synchronize()                                                       # the host reads the result
-
-    ag_steps = min(steps, 500)
-    for i in range(20):
-        ag_step(i)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(ag_steps):
-        ag_step(i)
-    torch.cuda.synchronize()
-    ag_s = time.perf_counter() - t0
-    ag_val = PX_PER_STEP * ag_steps / ag_s / 1e9            # per rank
-
-    # ---- per-kernel roofline numbers (rank 0 reports; every rank runs them to stay in step)
+    # ---- per-kernel numbers of the step (rank 0 reports; every rank runs them to stay in step)
     kit = max(50, min(steps, 400))
     lo_bytes = 4.0 * n_lo
     t_fwd = time_loop(fwd, kit, 20)
     t_bwd = time_loop(bwd, kit, 20)
-    # algorithmic bytes: fwd reads the logits, zero-fills dL/dlogits and writes the 16 B/pixel statistics
-    # cache; bwd reads logits + cache and accumulates dL/dlogits
-    fwd_bytes = 2 * lo_bytes + 16.0 * PX_PER_STEP
-    bwd_bytes = 2 * lo_bytes + 16.0 * PX_PER_STEP
+    # ALGORITHMIC bytes: the forward reads the low-resolution logits once (4 C h w per image); the backward
+    # reads them again and writes dL/dlogits (8 C h w).  The 16 B/pixel statistics cache between the two is this
+    # implementation's own traffic, NOT algorithmic: it is listed as `cache_bytes` and shows up in `traffic`.
+    fwd_bytes, bwd_bytes = lo_bytes, 2 * lo_bytes
+    cache_bytes = 16.0 * PX_PER_STEP
     kernels = [
         {"kernel": "fused_fwd_kernel<19,IW> + finalize_kernel", "bound": "issue/MUFU (not HBM)",
-         "algorithmic_bytes": fwd_bytes, "ms": t_fwd, "achieved_GBps": fwd_bytes / t_fwd / 1e6,
+         "algorithmic_bytes": fwd_bytes, "cache_bytes_written": cache_bytes, "ms": t_fwd, "achieved_GBps": fwd_bytes / t_fwd / 1e6,
          "frac_of_hbm": fwd_bytes / t_fwd / 1e6 / hbm_peak, "gpixel_per_s": PX_PER_STEP / t_fwd / 1e6},
         {"kernel": "fused_bwd_kernel<19,IW,cached>", "bound": "issue/MUFU (not HBM)",
-         "algorithmic_bytes": bwd_bytes, "ms": t_bwd, "achieved_GBps": bwd_bytes / t_bwd / 1e6,
+         "algorithmic_bytes": bwd_bytes, "cache_bytes_read": cache_bytes, "ms": t_bwd, "achieved_GBps": bwd_bytes / t_bwd / 1e6,
          "frac_of_hbm": bwd_bytes / t_bwd / 1e6 / hbm_peak, "gpixel_per_s": PX_PER_STEP / t_bwd / 1e6},
     ]
     extra = {}
     if not args.skip_secondary:
-        ch = confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak, dist)
+        c3 = cfg3_leg(lib, _lib, synth, mdist, comm, dev, stream, rank, world, dist, kit)
+        ch = confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak, dist, comm)
+        c5 = crosscity_leg(dev, rank, world, dist, comm)
         if rank == 0:
+            extra["cfg3_multi_level"] = c3
             extra["confusion_hist"] = ch
+            extra["cfg5_crosscity"] = c5
     if rank == 0 and world == 1 and not args.skip_secondary:        # per-GPU numbers: reported by the N = 1 run only
         kernels += secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit)
         extra["maxsquare"] = maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, aux_ptrs, acc_ptr, go_ptr, n_norm, stream, kit)
         extra["next_rows"] = next_rows(lib, _lib, synth, dev, stream, kit)
         extra["torch_cuda_eager_baseline"] = torch_eager_gpu(dev)
-        extra["crosscity_step"] = crosscity_step(dev)
     dom = max(kernels[:2], key=lambda k: k["ms"])
-    traffic, traffic_src = None, None
-    try:        # DRAM bytes of one launch from the committed ncu --set full capture of this workload
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        tk = tj["kernels"]["fused_fwd" if "fwd" in dom["kernel"] else "fused_bwd"]
-        traffic, traffic_src = tk["dram_read_bytes"] + tk["dram_write_bytes"], tj["source"]
-    except Exception:
-        pass
+    which = "fused_fwd" if "fwd" in dom["kernel"] else "fused_bwd"
+    traffic, traffic_src, tk = None, None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):       # DRAM bytes / instruction counts of one launch from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            tk = tj["kernels"][which]
+            traffic, traffic_src = tk["dram_read_bytes"] + tk["dram_write_bytes"], tj["source"]
+            break
+        except Exception:
+            continue
     issue = None
-    try:        # the bound that does apply: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock)
-        tk = tj["kernels"]["fused_fwd" if "fwd" in dom["kernel"] else "fused_bwd"]
-        peak_ginst = 148 * 4 * (clocks.get("sm_mhz") or 1965) / 1e3
-        issue = {"warp_instructions_per_launch": tk["warp_instructions"], "achieved_Ginst_per_s": tk["warp_instructions"] / dom["ms"] / 1e6,
-                 "peak_Ginst_per_s": peak_ginst, "frac": tk["warp_instructions"] / dom["ms"] / 1e6 / peak_ginst,
-                 "ncu_issue_active_pct": tk["issue_active_pct"], "ncu_pipes_pct": {"xu": tk["xu_pipe_pct"], "fma": tk["fma_pipe_pct"], "alu": tk["alu_pipe_pct"]},
+    if tk is not None:        # the bound that does apply: warp-instruction issue slots (SMs x 4 schedulers x SM clock)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_ginst = sms * 4 * (clocks.get("sm_mhz") or 1965) / 1e3
+        issue = {"kernel": dom["kernel"], "bound": "warp-instruction issue slots", "achieved": tk["warp_instructions"] / dom["ms"] / 1e6,
+                 "peak": peak_ginst, "unit": "Ginst/s", "frac": tk["warp_instructions"] / dom["ms"] / 1e6 / peak_ginst,
+                 "warp_instructions_per_launch": tk["warp_instructions"],
+                 "ncu_issue_active_pct": tk["issue_active_pct"],
+                 "ncu_pipes_pct": {"xu": tk["xu_pipe_pct"], "fma": tk["fma_pipe_pct"], "alu": tk["alu_pipe_pct"]},
+                 "source": traffic_src,
                  "note": "instruction count from the committed ncu capture; time = this run's CUDA-event time of the launch (incl. the "
-                         "dependent finalisation launch for the forward)"}
-    except Exception:
-        pass
+                         "dependent finalisation launch for the forward); peak = SMs x 4 schedulers x the SM clock sampled in this run"}
     roofline = {"bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom["achieved_GBps"] / hbm_peak, "traffic": traffic, "kernel": dom["kernel"],
-                "peak_source": peak_src,
-                "traffic_source": traffic_src, "issue_slots": issue,
-                "note": "the fused kernels move ~18 algorithmic B/pixel each (2.4 B of logits/gradient + the 16 B "
-                        "statistics cache) and are FP32-issue/MUFU bound by design (SURVEY.md 8d); the HBM-bound "
-                        "kernels of the path are listed under 'kernels'"}
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "launch_ms": dom["ms"],
+                "peak_source": peak_src, "traffic_source": traffic_src,
+                "note": "SURVEY 8d: 4*C*h*w bytes per image forward, 8*C*h*w backward (3.65 B/pixel for the pair); the fused "
+                        "kernels are FP32-issue/MUFU bound by design, so this fraction is ~1 % and `issue_roofline` is the binding "
+                        "figure; the HBM-bound kernels of the path (>= 70 % target) are listed under 'kernels' with their own fractions"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_baseline()
+        if "confusion_hist" in extra:
+            cpu["confusion_hist_port"] = cpu_eval_check(extra["confusion_hist"])
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warm_steps + REWARM, "warmup_requested": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "images_per_gpu": N_IMG, "global_batch": n_norm,
-                           "timing": "CUDA events around exactly `steps` steps on the launching stream, max over ranks; barrier + "
-                                     "synchronize on both sides, the last warm-up steps (as many as are timed) after the leading barrier",
-                           "l2_policy": f"inputs rotate over {POOL} distinct logits buffers "
-                                        f"({POOL * lo_bytes / 1e6:.0f} MB > 126 MB L2); outputs likewise",
-                           "hot_regime": {"ms_per_step": hot_ms, "value": world * PX_PER_STEP / hot_ms / 1e6,
-                                          "what": "4 buffer sets reused round-robin (inputs and statistics caches, 73 MB, stay in L2)"},
-                           "parallelism": f"image-sharded x{world}" + ("" if world == 1 else
-                               ", [loss,hist] of every step exchanged over NVLink peer-memory mailboxes by the step's own "
-                               "finalisation kernel (no NCCL call, no extra launch)" if comm.peer_memory else
-                               ", 1 NCCL all-reduce of [loss,hist] per step on the library's own communicator, "
-                               "overlapped with the next step")},
+                "config": shared_config(world),
+                "method": {
+                    "timing": "CUDA events around exactly `steps` steps on the launching stream, max over ranks; barrier + synchronize "
+                              f"on both sides; {warm_steps} warm-up steps before the leading barrier and {REWARM} after it, back to "
+                              "back with the timed ones",
+                    "l2_policy": f"inputs rotate over {POOL} distinct logits buffers ({POOL * lo_bytes / 1e6:.0f} MB > 126 MB L2); "
+                                 "outputs and statistics caches likewise",
+                    "hot_regime": {"ms_per_step": hot_ms, "value": world * PX_PER_STEP / hot_ms / 1e6,
+                                   "what": "4 buffer sets reused round-robin (inputs and statistics caches, 73 MB, stay in L2)"},
+                    "parallelism": f"image-sharded x{world}" + ("" if world == 1 else
+                        ", [loss,hist] of every step exchanged over NVLink peer-memory mailboxes by the step's own "
+                        "finalisation kernel (no NCCL call, no extra launch)" if comm.peer_memory else
+                        ", 1 ncclAllReduce of [loss,hist] per step on the library's own communicator, overlapped with the next step")},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lo_bytes),
-                        "d2h_bytes_per_step": int(lo_bytes) + 4, "steps": e2e_steps,
-                        "ms_per_step": e2e_s / e2e_steps * 1e3,
-                        "how": "HostPipeline.submit -> C ABI msq_pipe_submit (3-stream software pipeline): per step pinned host logits H2D, fused "
-                               f"fwd+bwd, loss + dL/dlogits D2H; {depth} steps in flight, host waits on step i-{depth} "
-                               "before reusing its buffers", "last_loss": last_loss,
-                        "autograd_per_rank": {"value": ag_val, "unit": UNIT, "steps": ag_steps,
-                                              "ms_per_step": ag_s / ag_steps * 1e3,
-                                              "how": "IW_MaxSquareloss nn.Module + autograd, H2D/D2H and a stream sync "
-                                                     "every step (Python overhead bound)"}},
-                "gpu_launches": 3 * steps,        # fused_fwd + finalize + fused_bwd per step (plus one memset)
-                "roofline": roofline, "kernels": kernels}
+                        "d2h_bytes_per_step": int(lo_bytes) + 4, "steps": api_steps, "ms_per_step": api_s * 1e3,
+                        "how": "the reference's API as tools/solve_gta5.py:199,217 call it: IW_MaxSquareloss nn.Module (C++ autograd "
+                               "node over the C ABI) -> (lambda_target * loss).backward(); per step pinned host logits H2D, loss + "
+                               f"dL/dlogits D2H to pinned memory; the host reads step i-{API_DEPTH}'s results when it reuses that slot "
+                               "(CUDA event), wall clock, max over ranks" + ("; each step also all-reduces [loss,hist] (StatsComm)" if world > 1 else ""),
+                        "last_loss": api_last_loss,
+                        "sync_every_step": {"value": world * PX_PER_STEP / api_sync_s / 1e9, "ms_per_step": api_sync_s * 1e3,
+                                            "how": "same, but the host waits for each step's loss + gradient before issuing the next"},
+                        "torch_floor": {"ms_per_step": floor_s * 1e3,
+                                        "how": "the same loop with x.sum() as the loss (one native kernel): PyTorch's own host cost of "
+                                               "detach + loss + lambda*loss + backward() + the copies, which bounds any nn.Module"},
+                        "c_abi_pipeline": {"value": pipe_val, "ms_per_step": pipe_s / pipe_steps * 1e3, "steps": pipe_steps,
+                                           "last_loss": pipe_last_loss,
+                                           "how": "HostPipeline.submit -> C ABI msq_pipe_submit (3-stream software pipeline, no autograd): "
+                                                  f"per step pinned host logits H2D, fused fwd+bwd, loss + dL/dlogits D2H; {depth} steps in "
+                                                  "flight" + ("; global normaliser + statistics exchange as in the device-timed loop" if world > 1 else "")}},
+                "gpu_launches": launches,
+                "gpu_launches_how": "counted by the library (msq_launch_count) over the timed region: fused forward + finalisation + "
+                                    "fused backward per step" + (" + one flush kernel at the closing join" if world > 1 else ""),
+                "roofline": roofline, "issue_roofline": issue, "kernels": kernels}
         line.update(extra)
+        for k in [k for k in line.get("confusion_hist", {}) if k.startswith("_")]:
+            del line["confusion_hist"][k]
+        if rank_spread is not None:
+            line["rank_spread"] = rank_spread
         if stats_check is not None:
             line["stats_check"] = stats_check
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak, dist):
+def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak, dist, comm):
     """cfg 4 (SYNTHIA->Cityscapes evaluation): Eval fast_hist + mIoU over 500 synthetic 512x1024 validation images,
     16 classes, sharded round-robin by image over the ranks (strong scaling: the 500 images are the job).  Each
-    rank accumulates its images into its own device matrix; one all-reduce of the C*C counts at the end; the
-    metrics are then read once.  Timed on the device with CUDA events, max over ranks.
-      per_image  one Eval.add_batch / msq_confusion_i64 launch per image, as tools/train_source.py:429-492 calls it
-      batched    the rank's images in launches of 16 (a caller that stacks its validation batch)
-      logits     per image from fp32 logits (1,16,512,1024): the callers' np.argmax fused into the kernel"""
+    rank accumulates its images into its own device matrix; ONE exact uint64 all-reduce of the C*C counts at the end
+    (the library's communicator: msq_comm_allreduce_u64); the metrics are then read once.  Timed on the device with
+    CUDA events, max over ranks.
+      per_image            one msq_confusion_i64 launch per image, as tools/train_source.py:429-492 calls add_batch
+      per_image_eval_api   the same through Eval.add_batch (the reference's API, one call per image)
+      eval_api_deferred16  Eval(defer=16).add_batch: the calls are queued and run 16 per launch (msq_confusion_i64_multi)
+      batched16            a caller that stacks its validation batch: 16 images per msq_confusion_i64 call
+      logits_per_image     per image from fp32 logits (1,16,512,1024): the callers' np.argmax fused into the kernel"""
     Cv, HWv, n_total, pool = 16, (512, 1024), 500, 128
     mine = list(range(rank, n_total, world))
     px_img = HWv[0] * HWv[1]
@@ -538,28 +644,27 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
     prs = {e: synth.noisy_prediction(gts[e].cpu(), Cv, 1000 + e).to(dev) for e in entries}
     gp, pp = {e: t.data_ptr() for e, t in gts.items()}, {e: t.data_ptr() for e, t in prs.items()}
     ev = msq.Eval(Cv, device=dev)
+    ev16 = msq.Eval(Cv, device=dev, defer=16)
     cm_ptr = ev._dev.data_ptr()
 
-    def timed(fn):
+    def timed(fn, e=ev):
         fn()                                                 # warm (also the clocks: the caller just ran the step loop)
-        ev.reset()
+        e.reset()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
-        if world > 1:
-            dist.all_reduce(ev.device_counts(), op=dist.ReduceOp.SUM)       # int64 counts over NCCL: exact
+        if comm is not None:
+            comm.allreduce_u64(e.device_counts())            # uint64 counts over NCCL/NVLink: exact
+            comm.join()
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        ev._pending = True
-        return ms, ev.Mean_Intersection_over_Union(), int(ev.confusion_matrix.sum())
+        ms = max_over_ranks(ms, dev, dist, world)
+        e._pending = True
+        return ms, e.Mean_Intersection_over_Union(), e.confusion_matrix.copy()
 
     def per_image():
         for i in mine:
@@ -571,6 +676,11 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
     def api_per_image():
         for i in mine:
             ev.add_batch(gts[i % pool], prs[i % pool])
+
+    def api_deferred():
+        for i in mine:
+            ev16.add_batch(gts[i % pool], prs[i % pool])
+        ev16.flush()
 
     B = 16
     groups = [entries[:B], entries[B:2 * B] if len(entries) >= 2 * B else entries[:B]]
@@ -598,17 +708,175 @@ def confusion_hist_leg(lib, _lib, synth, msq, dev, stream, rank, world, hbm_peak
                 _lib.check(rc)
 
     res = {"workload": f"cfg4 Eval over {n_total} synthetic 512x1024 val images, {Cv} classes (blocky gt, 30% noisy pred), "
-                       f"images sharded round-robin over {world} rank(s), one int64 all-reduce of the matrix at the end",
+                       f"images sharded round-robin over {world} rank(s), one exact uint64 all-reduce of the matrix at the end "
+                       "(msq_comm_allreduce_u64, the library's NCCL communicator)",
            "images": n_total, "scaling": "strong", "unit": UNIT}
     px_total = float(n_total) * px_img
-    for name, fn, bpp in (("per_image", per_image, 16.0), ("per_image_eval_api", api_per_image, 16.0),
-                          ("batched16", batched, 16.0), ("logits_per_image", logits, 4.0 * Cv + 8)):
-        ms, miou, total = timed(fn)
+    ref_cm = None
+    for name, fn, bpp, e in (("per_image", per_image, 16.0, ev), ("per_image_eval_api", api_per_image, 16.0, ev),
+                             ("eval_api_deferred16", api_deferred, 16.0, ev16), ("batched16", batched, 16.0, ev),
+                             ("logits_per_image", logits, 4.0 * Cv + 8, ev)):
+        ms, miou, cm = timed(fn, e)
         res[name] = {"value": px_total / ms / 1e6, "ms_total": ms, "us_per_image_per_rank": ms * 1e3 / len(mine),
                      "frac_of_hbm_aggregate": bpp * px_total / ms / 1e6 / (hbm_peak * world)}
         if name == "per_image":
+            ref_cm = cm
             res["miou_16_13"] = [float(miou[0]), float(miou[1])]
-            res["matrix_total"] = total
+            res["matrix_total"] = int(cm.sum())
+            res["matrix_sha1"] = __import__("hashlib").sha1(cm.astype("int64").tobytes()).hexdigest()
+        elif name in ("per_image_eval_api", "eval_api_deferred16"):
+            res[name]["matrix_equals_per_image"] = bool((cm == ref_cm).all())
+    res["_pool"], res["_classes"], res["_hw"] = pool, Cv, list(HWv)
+    return res
+
+
+def cpu_eval_check(ch):
+    """cpu_baseline leg (rank 0, N = 1): the cfg-4 matrix rebuilt by the NumPy port of the reference's ``Eval``
+    (oracle/eval_port.py) over the same 500 images -- equality with the GPU matrix, and the port's time."""
+    import hashlib
+    import numpy as np
+    from maxsquareloss_b200 import synth
+    from oracle import eval_port
+    pool, Cv, HWv, n_total = ch["_pool"], ch["_classes"], tuple(ch["_hw"]), ch["images"]
+    port = eval_port.EvalPort(Cv)
+    pairs = {}
+    t_port = 0.0
+    for i in range(n_total):
+        e = i % pool
+        if e not in pairs:
+            gt = synth.blocky_labels(1, HWv, Cv, 1000 + e)
+            pairs[e] = (gt.numpy(), synth.noisy_prediction(gt, Cv, 1000 + e).numpy())
+        t0 = time.perf_counter()
+        port.add_batch(*pairs[e])
+        t_port += time.perf_counter() - t0
+    cm = np.asarray(port.confusion_matrix)
+    miou = port.Mean_Intersection_over_Union()
+    return {"kind": "port", "cores": 1, "images": n_total, "value": n_total * HWv[0] * HWv[1] / t_port / 1e9, "unit": UNIT,
+            "ms_total": t_port * 1e3,
+            "matrix_bit_exact_vs_gpu": hashlib.sha1(cm.astype("int64").tobytes()).hexdigest() == ch["matrix_sha1"],
+            "miou_bit_exact_vs_gpu": [float(miou[0]), float(miou[1])] == ch["miou_16_13"]}
+
+
+def cfg3_leg(lib, _lib, synth, mdist, comm, dev, stream, rank, world, dist, kit):
+    """BASELINE config 3: MaxSquare+IW+Multi (tools/solve_gta5.py:178-218 with --multi): IW-MaxSquare on head 1 +
+    self-produced guidance cross-entropy on head 2, GLOBAL batch 8 strong-sharded over the ranks (8/G images each).
+    Per step and rank: msq_multi_fwd (both heads, one kernel + finalisation), the exact uint64 all-reduce of the
+    [cross-entropy sum | valid-pixel count] pair forked right after it (the head-2 backward divides by the GLOBAL count),
+    msq_fused_bwd for head 1 (overlaps the collective), join, msq_guidance_bwd for head 2; the [loss | hist] vector of
+    head 1 is all-reduced as well.  check: the all-reduced integers against ONE GPU computing all 8 images."""
+    NG, thr = 8, 0.95
+    if NG % world:
+        return {"skipped": f"global batch {NG} does not divide over {world} ranks"}
+    lo_i, hi_i = mdist.image_shard(NG, rank, world)
+    nl = hi_i - lo_i
+    h, w = HW_LO
+    H, W = HW_OUT
+    pool = 6
+    full1 = [synth.head_logits(NG, C, HW_LO, 7000 + p, 5.0) for p in range(pool)]
+    full2 = [synth.second_head(full1[p], 7000 + p) for p in range(pool)]
+    lo1 = [t[lo_i:hi_i].contiguous().to(dev) for t in full1]
+    lo2 = [t[lo_i:hi_i].contiguous().to(dev) for t in full2]
+    g1, g2 = [torch.empty_like(t) for t in lo1], [torch.empty_like(t) for t in lo2]
+    lay = _lib.state_layout(nl, C)
+    accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev)
+    outs = [torch.empty(lay.out_bytes, dtype=torch.uint8, device=dev) for _ in range(pool)]
+    nb = lib.msq_fused_aux_bytes(nl, H, W)
+    naux = max(2, min(pool, int(200e6 // (2 * nb)) + 1))
+    aux1 = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(naux)]
+    aux2 = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(naux)]
+    go = torch.full((), LAMBDA_TARGET, device=dev)
+    go2 = torch.full((), LAMBDA_TARGET * 0.1, device=dev)                 # lambda_seg * lambda_target (train_source.py:827)
+    comm_h = comm._h if comm is not None else None
+
+    def run(j, l1, l2, o, a1, a2, gr1, gr2, n, acc, sharded):
+        rc = lib.msq_multi_fwd(_lib.MODE_IW, l1.data_ptr(), l2.data_ptr(), n, C, h, w, H, W, RATIO, thr, NG,
+                               acc.data_ptr(), o.data_ptr(), a1.data_ptr(), a2.data_ptr(), gr1.data_ptr(), gr2.data_ptr(), None, stream)
+        if rc:
+            _lib.check(rc)
+        if sharded:
+            _lib.check(lib.msq_comm_allreduce_u64(comm_h, o.data_ptr() + lay_of(n).ce_fix_out_off, 2, stream))
+        rc = lib.msq_fused_bwd(_lib.MODE_IW, l1.data_ptr(), n, C, h, w, H, W, NG, o.data_ptr(), a1.data_ptr(), go.data_ptr(),
+                               gr1.data_ptr(), 1, stream)
+        if rc:
+            _lib.check(rc)
+        if sharded:
+            _lib.check(lib.msq_comm_join(comm_h, 0, stream))
+        rc = lib.msq_guidance_bwd(l2.data_ptr(), n, C, h, w, H, W, o.data_ptr(), a2.data_ptr(), go2.data_ptr(), gr2.data_ptr(), 1, stream)
+        if rc:
+            _lib.check(rc)
+        if sharded:
+            _lib.check(lib.msq_comm_allreduce_f64(comm_h, o.data_ptr() + lay_of(n).stats_off, 1 + C, stream))
+
+    def lay_of(n):
+        return _lib.state_layout(n, C)
+
+    sharded = comm is not None
+
+    def step(i):
+        j = i % pool
+        run(j, lo1[j], lo2[j], outs[j], aux1[i % naux], aux2[i % naux], g1[j], g2[j], nl, accum, sharded)
+
+    it = max(30, min(kit, 200))
+    for i in range(20):
+        step(i)
+    if sharded:
+        comm.join()
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(it):
+        step(i)
+    if sharded:
+        comm.join()
+    b.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b) / it, dev, dist, world)
+    px = NG * H * W
+    res = {"what": "cfg3 MaxSquare+IW+Multi step (tools/solve_gta5.py:178-218 --multi): IW-MaxSquare head 1 + guidance CE head 2, "
+                   f"forward + both backwards, global batch {NG} strong-sharded over {world} rank(s) ({nl} images each), "
+                   "65x129 -> 512x1024, thr 0.95, lambda 0.1/0.1",
+           "scaling": "strong", "us_per_step": ms * 1e3, "value": px / ms / 1e6, "unit": UNIT, "launches_per_step": 4,
+           "exchange": None if not sharded else "exact uint64 ncclAllReduce of [ce_fix | nvalid] between forward and head-2 backward "
+                                                "(overlapped with the head-1 backward) + fp64 ncclAllReduce of [loss | hist], library communicator"}
+    # ---- parity of the sharded step against ONE GPU doing all 8 images (pool entry 0)
+    step(0)
+    if sharded:
+        comm.join()
+    torch.cuda.synchronize()
+    o = outs[0]
+    pair = o[lay.ce_fix_out_off:lay.ce_fix_out_off + 16].view(torch.int64).clone()
+    stats = o[lay.stats_off:lay.stats_off + 8 * (1 + C)].view(torch.float64).clone()
+    grad1_mine, grad2_mine = g1[0].clone(), g2[0].clone()
+    if sharded:
+        layf = _lib.state_layout(NG, C)
+        f1, f2 = full1[0].to(dev), full2[0].to(dev)
+        fg1, fg2 = torch.empty_like(f1), torch.empty_like(f2)
+        facc = torch.zeros(layf.accum_bytes, dtype=torch.uint8, device=dev)
+        fo = torch.empty(layf.out_bytes, dtype=torch.uint8, device=dev)
+        fnb = lib.msq_fused_aux_bytes(NG, H, W)
+        fa1, fa2 = torch.empty(fnb, dtype=torch.uint8, device=dev), torch.empty(fnb, dtype=torch.uint8, device=dev)
+        run(0, f1, f2, fo, fa1, fa2, fg1, fg2, NG, facc, False)
+        torch.cuda.synchronize()
+        rpair = fo[layf.ce_fix_out_off:layf.ce_fix_out_off + 16].view(torch.int64)
+        rstats = fo[layf.stats_off:layf.stats_off + 8 * (1 + C)].view(torch.float64)
+        rel = lambda x, y: abs(float(x) - float(y)) / max(abs(float(y)), 1e-300)          # noqa: E731
+        gmax = lambda x, y: float((x - y).abs().max() / y.abs().max().clamp_min(1e-30))   # noqa: E731
+        chk = {"label2_valid_count_bit_exact": bool(int(pair[1]) == int(rpair[1])), "label2_valid_count": int(pair[1]),
+               "class_hist_bit_exact": bool(torch.equal(stats[1:], rstats[1:])),
+               "ce_sum_rel": rel(pair[0], rpair[0]), "loss_head1_rel": rel(stats[0], rstats[0]),
+               "grad_head1_max_rel": gmax(grad1_mine, fg1[lo_i:hi_i]), "grad_head2_max_rel": gmax(grad2_mine, fg2[lo_i:hi_i]),
+               "reference": "the same 8 images on ONE GPU (this rank), same kernels, n_images_norm = 8"}
+        ok = (chk["label2_valid_count_bit_exact"] and chk["class_hist_bit_exact"] and chk["ce_sum_rel"] <= 1e-6 and
+              chk["loss_head1_rel"] <= 1e-6 and chk["grad_head1_max_rel"] <= 1e-4 and chk["grad_head2_max_rel"] <= 1e-4)
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        chk["ok"] = bool(int(okt.item()) == 1)
+        res["check"] = chk
+        del f1, f2, fg1, fg2, fa1, fa2
+    else:
+        res["reference_values"] = {"label2_valid_count": int(pair[1]), "ce_sum": float(pair[0]) * 2.0 ** -32,
+                                   "loss_head1": float(stats[0]), "class_hist_total": float(stats[1:].sum())}
     return res
 
 
@@ -736,27 +1004,32 @@ def next_rows(lib, _lib, synth, dev, stream, kit):
     return res
 
 
-def crosscity_step(dev, iters=8):
-    """BASELINE config 5 on one GPU: the adaptation step of tools/solve_crosscity.py:165-249 (no --multi) around a
-    random-init DeepLabv2-ResNet101 (harness/deeplabv2.py: the reference's topology, cuDNN, NOT the product), batch 1,
-    13 classes, 512x1024, SGD step included.  'fused' = low-resolution heads into CrossEntropyLoss2d(+Eval) and
-    IW_MaxSquareloss; 'reference_chain' = the same step with the model's two F.interpolate calls, torch softmax /
-    cross-entropy, the oracle port of IW_MaxSquareloss (per-image D2H + CPU histc + H2D) and the callers' D2H of the
-    logits + np.argmax + Eval.add_batch (numpy port).  torch defaults (TF32 convolutions) in both."""
+def crosscity_leg(dev, rank, world, dist, comm, iters=8):
+    """BASELINE config 5: the adaptation step of tools/solve_crosscity.py:165-249 (no --multi) around a random-init
+    DeepLabv2-ResNet101 (harness/deeplabv2.py: the reference's topology, cuDNN, NOT the product), 13 classes, 512x1024,
+    batch 1 per GPU, SGD step included.  'fused' = low-resolution heads into CrossEntropyLoss2d(+Eval) and
+    IW_MaxSquareloss.  One GPU: also 'reference_chain' = the same step with the model's two F.interpolate calls, torch
+    softmax / cross-entropy, the oracle port of IW_MaxSquareloss (per-image D2H + CPU histc + H2D) and the callers' D2H of
+    the logits + np.argmax + Eval.add_batch (numpy port), and the backbone alone.  N GPUs: every rank steps its own image
+    (same initial weights); the loss normaliser is the global batch, the source cross-entropy averages over the valid
+    pixels of ALL ranks (exact uint64 all-reduce, StatsComm) and the confusion matrix is all-reduced at the end; the
+    backbone-gradient all-reduce is DDP's job and not part of the path.  torch defaults (TF32 convolutions)."""
     import numpy as np
     import torch.nn.functional as F
     import maxsquareloss_b200 as msq
     from harness.deeplabv2 import DeepLabV2Harness
-    from oracle import eval_port, loss_port
+    from maxsquareloss_b200 import synth
     C5, HW5 = 13, (512, 1024)
     torch.manual_seed(12345)
     model = DeepLabV2Harness(C5).to(dev).train()
     opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=2.5e-4, momentum=0.9, weight_decay=5e-4)
-    xs, xt = torch.randn(1, 3, *HW5, device=dev), torch.randn(1, 3, *HW5, device=dev)
-    from maxsquareloss_b200 import synth
-    ys = synth.blocky_labels(1, HW5, C5, 5).to(dev)
-    ev, port = msq.Eval(C5, device=dev), eval_port.EvalPort(C5)
-    ce, iw = msq.CrossEntropyLoss2d(ignore_index=-1), msq.IW_MaxSquareloss(-1, C5, 0.2)
+    gs = torch.Generator().manual_seed(500 + rank)
+    xs, xt = torch.randn(1, 3, *HW5, generator=gs).to(dev), torch.randn(1, 3, *HW5, generator=gs).to(dev)
+    ys = synth.blocky_labels(1, HW5, C5, 5 + rank).to(dev)
+    ev = msq.Eval(C5, device=dev)
+    ce = msq.CrossEntropyLoss2d(ignore_index=-1, group=comm if comm is not None else False)
+    iw = msq.IW_MaxSquareloss(-1, C5, 0.2)
+    iw.global_batch = world
 
     def fused():
         lo, _ = model(xs)
@@ -766,35 +1039,68 @@ def crosscity_step(dev, iters=8):
         opt.step()
         opt.zero_grad()
 
-    def ref():
-        pred, _ = model(xs, upsample=True)
-        F.cross_entropy(pred, ys, ignore_index=-1).backward()
-        port.add_batch(ys.cpu().numpy(), np.argmax(pred.data.cpu().numpy(), axis=1))
-        tp, _ = model(xt, upsample=True)
-        (0.1 * loss_port.iw_maxsquare(F.softmax(tp, 1), C5, 0.2)).backward()
-        opt.step()
-        opt.zero_grad()
-
-    def backbone_only():
-        lo, _ = model(xs)
-        lo.sum().backward()
-        lt, _ = model(xt)
-        lt.sum().backward()
-        opt.step()
-        opt.zero_grad()
-
-    out = {"what": "cfg5 adaptation step on one GPU (source CE + Eval, target IW-MaxSquare, SGD), DeepLabv2-ResNet101 "
-                   "random init on cuDNN, batch 1, 13 classes, 512x1024; ms per step"}
-    for name, fn in (("fused_ms", fused), ("reference_chain_ms", ref), ("backbone_only_ms", backbone_only)):
+    def timeit(fn):
         for _ in range(3):
             fn()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(iters):
             fn()
         torch.cuda.synchronize()
-        out[name] = (time.perf_counter() - t0) / iters * 1e3
-    out["miou_fused"] = float(ev.Mean_Intersection_over_Union())
+        return max_over_ranks((time.perf_counter() - t0) / iters * 1e3, dev, dist, world)
+
+    out = {"what": f"cfg5 adaptation step (source CE + Eval, target IW-MaxSquare, SGD), DeepLabv2-ResNet101 random init on cuDNN, "
+                   f"batch 1 per GPU x {world} GPU(s), 13 classes, 512x1024; ms per step, max over ranks",
+           "scaling": "weak", "fused_ms": timeit(fused)}
+    out["images_per_s"] = world / (out["fused_ms"] * 1e-3)
+    if world == 1:
+        from oracle import eval_port, loss_port
+        port = eval_port.EvalPort(C5)
+
+        def ref():
+            pred, _ = model(xs, upsample=True)
+            F.cross_entropy(pred, ys, ignore_index=-1).backward()
+            port.add_batch(ys.cpu().numpy(), np.argmax(pred.data.cpu().numpy(), axis=1))
+            tp, _ = model(xt, upsample=True)
+            (0.1 * loss_port.iw_maxsquare(F.softmax(tp, 1), C5, 0.2)).backward()
+            opt.step()
+            opt.zero_grad()
+
+        def backbone_only():
+            lo, _ = model(xs)
+            lo.sum().backward()
+            lt, _ = model(xt)
+            lt.sum().backward()
+            opt.step()
+            opt.zero_grad()
+        out["reference_chain_ms"] = timeit(ref)
+        out["backbone_only_ms"] = timeit(backbone_only)
+        out["miou_fused"] = float(ev.Mean_Intersection_over_Union())
+    else:
+        # the exchange of the evaluation counts: every rank's local matrix of ONE more forward, all-reduced through the
+        # library (exact uint64) against the sum of the all-gathered local matrices
+        ev.reset()
+        with torch.no_grad():
+            lo, _ = model(xs)
+            ce(lo, ys, evaluator=ev)               # the fused source kernel: CE + argmax + confusion matrix of this rank's image
+        local = ev.device_counts().clone()
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        expect = torch.stack(parts).sum(0)
+        comm.allreduce_u64(ev.device_counts())
+        comm.join()
+        torch.cuda.synchronize()
+        got = ev.device_counts().clone()
+        ev._pending = True
+        okm = bool(torch.equal(got, expect))
+        okt = torch.tensor([1 if okm else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        out["check"] = {"confusion_matrix_allreduce_bit_exact": bool(int(okt.item()) == 1), "matrix_total": int(got.sum()),
+                        "miou": float(ev.Mean_Intersection_over_Union()),
+                        "ce_global_valid_pixels": int(ce.last_nvalid.item()),
+                        "ok": bool(int(okt.item()) == 1)}
     del model, opt
     torch.cuda.empty_cache()
     return out

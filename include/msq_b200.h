@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSQ_ABI_VERSION 5
+#define MSQ_ABI_VERSION 6
 #define MSQ_MAX_CLASSES 32          /* reference uses 13 / 16 / 19 */
 
 #define MSQ_E_BADARG   (-1)         /* null pointer, non-positive size, C > MSQ_MAX_CLASSES */
@@ -88,14 +88,17 @@ unsigned long long msq_launch_count(void);
  *   loss2     float32      msq_multi_fwd: CrossEntropyLoss(ignore_index=-1)(head 2, label_2)
  *   ce_out    float64      msq_multi_fwd: sum over those pixels of -log softmax(head 2)[label_2];
  *                          loss2 = ce_out / nvalid_out.  When images are sharded over ranks the
- *                          caller all-reduces {ce_out, nvalid_out} and stores the global count back
- *                          into nvalid_out before msq_guidance_bwd (which divides by it)
+ *                          caller all-reduces the pair below in place before msq_guidance_bwd (which
+ *                          divides by nvalid_out) and forms loss2 = ce_fix_out * 2^-32 / nvalid_out
+ *   ce_fix_out uint64      the same sum as the 2^-32 fixed-point integer it was accumulated in;
+ *                          [ce_fix_out, nvalid_out] are ADJACENT: one exact integer all-reduce of 2 words
+ *                          (msq_comm_allreduce_u64) gives the cross-entropy mean of the GLOBAL batch
  * ------------------------------------------------------------------------- */
 typedef struct msq_state_layout {
     int64_t sumsq_off, kept_off, hist_off, flags_off, ticket_off, ce_off, nvalid_off;   /* into accum */
     int64_t accum_bytes;
     int64_t sum_out_off, kept_out_off, loss_off, weights_off, hist_out_off, stats_off,
-            nvalid_out_off, loss2_off, ce_out_off;                                                /* into out */
+            ce_fix_out_off, nvalid_out_off, loss2_off, ce_out_off;                                /* into out */
     int64_t out_bytes;
 } msq_state_layout;
 
@@ -284,6 +287,11 @@ int  msq_pipe_create(int mode, int n, int num_class, int h, int w, int out_h, in
                      double ratio, int depth, msq_pipe** out);
 int  msq_pipe_submit(msq_pipe* pipe, const float* host_logits, float grad_scale, float* host_loss,
                      float* host_grad /* nullable */, int32_t* host_hist /* nullable */, int* slot_out);
+/* Images sharded over ranks: the steps use n_images_norm (the GLOBAL batch size) as the loss normaliser and exchange
+ * their [loss | class histogram] vector through comm (msq_comm_*, below; NULL: no exchange), exactly as
+ * msq_fused_fwd_bwd does.  Call once, before the first submit, on every rank. */
+struct msq_comm;
+int  msq_pipe_shard(msq_pipe* pipe, int n_images_norm, struct msq_comm* comm);
 int  msq_pipe_wait(msq_pipe* pipe, int slot);
 int  msq_pipe_drain(msq_pipe* pipe);
 void msq_pipe_destroy(msq_pipe* pipe);
@@ -306,6 +314,9 @@ typedef struct msq_comm msq_comm;
 int msq_comm_unique_id(void* id128 /* host, 128 bytes */);
 int msq_comm_create(const void* id128, int world, int rank, msq_comm** out);
 int msq_comm_allreduce_f64(msq_comm* comm, double* buf /* device, in place */, int count, msq_stream_t stream);
+/* the same for the path's INTEGER results (confusion counts of Eval, utils/eval.py:121; the adjacent
+ * [ce_fix_out | nvalid_out] pair of the cross-entropy rows): uint64 words, exact whatever the order of the sum */
+int msq_comm_allreduce_u64(msq_comm* comm, unsigned long long* buf /* device, in place */, int count, msq_stream_t stream);
 int msq_comm_join(msq_comm* comm, int lag /* 0 = most recent all-reduce, k = k calls earlier (< 8) */, msq_stream_t stream);
 void msq_comm_destroy(msq_comm* comm);
 

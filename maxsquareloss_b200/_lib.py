@@ -17,16 +17,16 @@ MODE_IW = 1
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_launch_count", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
            "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_i64_multi", "msq_confusion_per_image_logits_f32", "msq_softce_fwd", "msq_softce_bwd", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
-           "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_join", "msq_comm_destroy",
+           "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_allreduce_u64", "msq_comm_join", "msq_comm_destroy",
            "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_enable", "msq_comm_box_active", "msq_comm_box_errors", "msq_comm_box_timeout", "msq_comm_result",
-           "msq_pipe_create", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
+           "msq_pipe_create", "msq_pipe_shard", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
 
 class StateLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "sumsq_off", "kept_off", "hist_off", "flags_off", "ticket_off", "ce_off", "nvalid_off", "accum_bytes",
         "sum_out_off", "kept_out_off", "loss_off", "weights_off", "hist_out_off", "stats_off",
-        "nvalid_out_off", "loss2_off", "ce_out_off", "out_bytes")]
+        "ce_fix_out_off", "nvalid_out_off", "loss2_off", "ce_out_off", "out_bytes")]
 
 
 _lib = None
@@ -95,6 +95,8 @@ def load():
         lib.msq_tune_set.argtypes = [c.c_char_p, i32]
         lib.msq_pipe_create.restype = i32
         lib.msq_pipe_create.argtypes = [i32, i32, i32, i32, i32, i32, i32, dbl, i32, c.POINTER(vp)]
+        lib.msq_pipe_shard.restype = i32
+        lib.msq_pipe_shard.argtypes = [vp, i32, vp]
         lib.msq_pipe_submit.restype = i32
         lib.msq_pipe_submit.argtypes = [vp, vp, c.c_float, vp, vp, vp, c.POINTER(i32)]
         lib.msq_pipe_wait.restype = i32
@@ -109,6 +111,8 @@ def load():
         lib.msq_comm_create.argtypes = [vp, i32, i32, c.POINTER(vp)]
         lib.msq_comm_allreduce_f64.restype = i32
         lib.msq_comm_allreduce_f64.argtypes = [vp, vp, i32, vp]
+        lib.msq_comm_allreduce_u64.restype = i32
+        lib.msq_comm_allreduce_u64.argtypes = [vp, vp, i32, vp]
         lib.msq_comm_join.restype = i32
         lib.msq_comm_join.argtypes = [vp, i32, vp]
         lib.msq_comm_box_export.restype = i32
@@ -129,7 +133,7 @@ def load():
         lib.msq_comm_destroy.argtypes = [vp]
         lib.msq_pipe_destroy.restype = None
         lib.msq_pipe_destroy.argtypes = [vp]
-        if lib.msq_abi_version() != 5:
+        if lib.msq_abi_version() != 6:
             raise RuntimeError("libmsq_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -58,7 +58,10 @@ def build_torch_binding(force=False):
         return TORCH_LIB
     import torch
     tdir = os.path.dirname(os.path.abspath(torch.__file__))
-    cxx = os.environ.get("CXX") or shutil.which("g++")
+    # the SYSTEM g++ (the one whose libstdc++.so.6 PyTorch runs on).  $CXX is deliberately ignored: this image exports a
+    # CXX whose libstdc++ is linked statically, and a binding with a private copy of the iostreams crashes inside
+    # TORCH_CHECK's message formatting (seen on the B200 box: SIGSEGV in std::ostream::_M_insert<long>)
+    cxx = os.environ.get("MSQ_CXX") or next((c for c in ("/usr/bin/g++", shutil.which("g++")) if c and os.path.exists(c)), None)
     if not cxx:
         raise RuntimeError("g++ not found: libmsq_torch.so cannot be built")
     cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
@@ -69,6 +72,9 @@ def build_torch_binding(force=False):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr[-4000:])
+    needed = subprocess.run(["readelf", "-d", TORCH_LIB + ".tmp"], capture_output=True, text=True).stdout
+    if "libstdc++.so" not in needed:
+        raise RuntimeError(f"{cxx} linked libstdc++ statically into libmsq_torch.so; set MSQ_CXX to the system g++")
     os.replace(TORCH_LIB + ".tmp", TORCH_LIB)
     return TORCH_LIB
 

@@ -50,7 +50,7 @@ const NcclApi& nccl() {
     return api;
 }
 
-constexpr int kNcclFloat64 = 8, kNcclSum = 0;      // nccl.h: ncclDataType_t / ncclRedOp_t
+constexpr int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0;      // nccl.h: ncclDataType_t / ncclRedOp_t
 constexpr int kRing = 8;
 
 }  // namespace
@@ -149,15 +149,27 @@ extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm*
 // Enqueue all-reduce(sum) of buf[0..count) (device fp64, in place) after everything already enqueued on
 // `stream`; returns at once.  The result may be read by work enqueued on `stream` after msq_comm_join.
 // The buffer must stay allocated and untouched until then (the collective runs on the communicator's side stream).
-extern "C" int msq_comm_allreduce_f64(msq_comm* c, double* buf, int count, msq_stream_t stream) {
+static int comm_allreduce(msq_comm* c, void* buf, int count, int nccl_type, msq_stream_t stream) {
     if (!c || !buf || count < 1) return MSQ_E_BADARG;
+    if (((uintptr_t)buf) & 7u) return MSQ_E_ALIGN;
     cudaError_t e;
     if ((e = cudaEventRecord(c->fork, (cudaStream_t)stream)) != cudaSuccess) return (int)e;
     if ((e = cudaStreamWaitEvent(c->side, c->fork, 0)) != cudaSuccess) return (int)e;
-    if (nccl().all_reduce(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->side) != 0) return MSQ_E_NCCL;
+    if (nccl().all_reduce(buf, buf, (size_t)count, nccl_type, kNcclSum, c->comm, c->side) != 0) return MSQ_E_NCCL;
     if ((e = cudaEventRecord(c->done[c->issued % kRing], c->side)) != cudaSuccess) return (int)e;
     c->issued++;
     return 0;
+}
+
+extern "C" int msq_comm_allreduce_f64(msq_comm* c, double* buf, int count, msq_stream_t stream) {
+    return comm_allreduce(c, buf, count, kNcclFloat64, stream);
+}
+
+// The integer results of the path -- the C x C confusion counts of Eval (utils/eval.py:121), the {cross-entropy sum in
+// 2^-32 fixed point, valid-pixel count} pair of the guidance / source cross-entropy rows -- all-reduced as the uint64
+// words they are: exact, and independent of the order NCCL adds them in.  Same stream semantics as the fp64 call.
+extern "C" int msq_comm_allreduce_u64(msq_comm* c, unsigned long long* buf, int count, msq_stream_t stream) {
+    return comm_allreduce(c, buf, count, kNcclUint64, stream);
 }
 
 // Make `stream` wait for the all-reduce issued `lag` calls before the most recent one (lag 0 = the most

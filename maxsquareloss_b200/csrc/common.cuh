@@ -38,6 +38,7 @@ struct State {
     float* loss2;                  // out
     unsigned long long* nvalid_out;
     double* ce_out;                // out: sum of -log p2[label_2] over the valid pixels (for sharded means)
+    unsigned long long* ce_fix_out;   // out: the same sum as the 2^-32 fixed-point integer it was accumulated in (exact to all-reduce)
 };
 
 // SM count of the CURRENT device (a process may drive several GPUs: cached per ordinal)
@@ -82,6 +83,8 @@ inline msq_state_layout make_layout(int n, int c) {
     L.hist_out_off = off; off += nc * 4;
     off = align_up(off, 16);
     L.stats_off = off;    off += (int64_t)(1 + c) * 8;
+    off = align_up(off, 16);
+    L.ce_fix_out_off = off; off += 8;      // [ce_fix_out | nvalid_out]: one contiguous uint64 pair (all-reduced as such)
     L.nvalid_out_off = off; off += 8;
     L.loss2_off = off;    off += 4;
     off = align_up(off, 8);
@@ -111,6 +114,7 @@ inline State carve(void* accum, void* out, int n, int c) {
     s.loss2 = (float*)(o + L.loss2_off);
     s.nvalid_out = (unsigned long long*)(o + L.nvalid_out_off);
     s.ce_out = (double*)(o + L.ce_out_off);
+    s.ce_fix_out = (unsigned long long*)(o + L.ce_fix_out_off);
     return s;
 }
 
@@ -267,6 +271,7 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
             *st.loss2 = (float)l2;
             *st.nvalid_out = nv_ld;
             *st.ce_out = (double)ce_ld * kInvFix;
+            *st.ce_fix_out = ce_ld;
         }
         *st.kept = 0ull;                       // self-clean
         *st.flags = 0u;

@@ -28,6 +28,8 @@ struct msq_pipe {
         bool busy;
     } * slots;
     unsigned long long submitted;
+    int n_norm;                 // normaliser when the batch is sharded by image over ranks (0: this pipeline's own n)
+    msq_comm* comm;             // statistics exchange of the sharded step (NULL: none)
 };
 
 static void pipe_free(msq_pipe* p) {
@@ -65,6 +67,7 @@ extern "C" int msq_pipe_create(int mode, int n, int num_class, int h, int w, int
     if (!p) return (int)cudaErrorMemoryAllocation;
     p->mode = mode; p->n = n; p->C = num_class; p->h = h; p->w = w; p->H = out_h; p->W = out_w;
     p->depth = depth; p->ratio = ratio; p->submitted = 0;
+    p->n_norm = 0; p->comm = nullptr;
     p->lo_bytes = (size_t)n * num_class * h * w * sizeof(float);
     p->lay = make_layout(n, num_class);
     p->slots = new (std::nothrow) msq_pipe::Slot[depth]();
@@ -116,14 +119,16 @@ extern "C" int msq_pipe_submit(msq_pipe* p, const float* host_logits, float grad
     if ((e = cudaEventRecord(s.staged, p->s_h2d)) != cudaSuccess) return (int)e;
     // stage 2 (SMs): all steps' kernels in submission order on one stream
     if ((e = cudaStreamWaitEvent(p->s_comp, s.staged, 0)) != cudaSuccess) return (int)e;
-    rc = fused_fwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, nullptr, p->ratio, 0, s.d_accum,
-                            s.d_out, host_grad ? s.d_aux : nullptr, host_grad ? s.d_grad : nullptr, p->s_comp);
-    if (rc) return rc;
     if (host_grad) {
-        rc = fused_bwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, 0, s.d_out, nullptr, grad_scale,
-                                s.d_grad, s.d_aux, 1, p->s_comp);
-        if (rc) return rc;
+        // the one-call step: forward -> finalise -> backward and, when the images are sharded over ranks, the exchange
+        // of [loss | class histogram] (peer-memory mailboxes inside the finalisation kernel, or ncclAllReduce)
+        rc = msq_fused_fwd_bwd(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, p->ratio, p->n_norm, s.d_accum,
+                               s.d_out, s.d_aux, nullptr, grad_scale, s.d_grad, p->comm, 0, (msq_stream_t)p->s_comp);
+    } else {
+        rc = fused_fwd_dispatch(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, nullptr, p->ratio, p->n_norm,
+                                s.d_accum, s.d_out, nullptr, nullptr, p->s_comp);
     }
+    if (rc) return rc;
     if ((e = cudaEventRecord(s.computed, p->s_comp)) != cudaSuccess) return (int)e;
     // stage 3 (the other copy engine): outputs -> host
     if ((e = cudaStreamWaitEvent(p->s_d2h, s.computed, 0)) != cudaSuccess) return (int)e;
@@ -141,12 +146,22 @@ extern "C" int msq_pipe_submit(msq_pipe* p, const float* host_logits, float grad
     return 0;
 }
 
+// Images sharded over ranks: every step uses the GLOBAL batch size as the loss normaliser and exchanges its statistics
+// vector through `comm` (msq_fused_fwd_bwd).  Call between msq_pipe_create and the first submit, on every rank.
+extern "C" int msq_pipe_shard(msq_pipe* p, int n_images_norm, msq_comm* comm) {
+    if (!p || n_images_norm < 0 || p->submitted) return MSQ_E_BADARG;
+    p->n_norm = n_images_norm;
+    p->comm = comm;
+    return 0;
+}
+
 extern "C" int msq_pipe_drain(msq_pipe* p) {
     if (!p) return MSQ_E_BADARG;
     for (int i = 0; i < p->depth; ++i) {
         const int rc = msq_pipe_wait(p, i);
         if (rc) return rc;
     }
+    if (p->comm) return msq_comm_join(p->comm, 0, (msq_stream_t)p->s_comp);       // completes the two steps still in flight
     return 0;
 }
 

@@ -153,6 +153,15 @@ class StatsComm:
         stream = torch.cuda.current_stream(buf.device).cuda_stream
         self._libmod.check(self._lib.msq_comm_allreduce_f64(self._h, buf.data_ptr(), buf.numel(), stream))
 
+    def allreduce_u64(self, buf):
+        """Sum the int64/uint64 CUDA vector ``buf`` over the ranks, in place (exact): the confusion counts of ``Eval``,
+        the ``[ce_fix | nvalid]`` pair of the cross-entropy rows.  Asynchronous like ``allreduce``; ``join()`` orders the
+        current stream after it."""
+        if not (buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous()):
+            raise RuntimeError("StatsComm.allreduce_u64 needs a contiguous int64 CUDA tensor")
+        stream = torch.cuda.current_stream(buf.device).cuda_stream
+        self._libmod.check(self._lib.msq_comm_allreduce_u64(self._h, buf.data_ptr(), buf.numel(), stream))
+
     def allreduce_ptr(self, ptr, count, stream):
         rc = self._lib.msq_comm_allreduce_f64(self._h, ptr, count, stream)
         if rc:

@@ -14,7 +14,7 @@ from . import _lib
 
 
 class HostPipeline:
-    def __init__(self, mode, n, num_class, hw_in, hw_out, ratio=0.2, depth=3, device=None):
+    def __init__(self, mode, n, num_class, hw_in, hw_out, ratio=0.2, depth=3, device=None, comm=None, global_batch=0):
         if not torch.cuda.is_available():
             raise RuntimeError("HostPipeline needs a CUDA device: there is no CPU fallback")
         if device is not None:
@@ -28,6 +28,9 @@ class HostPipeline:
         _lib.check(self._lib.msq_pipe_create(self.mode, n, num_class, int(hw_in[0]), int(hw_in[1]), int(hw_out[0]),
                                              int(hw_out[1]), float(ratio), depth, ctypes.byref(h)))
         self._h = h
+        self._comm = comm                  # dist.StatsComm: images sharded over ranks (kept alive with the pipeline)
+        if comm is not None or global_batch:
+            _lib.check(self._lib.msq_pipe_shard(h, int(global_batch), comm._h if comm is not None else None))
         self._ok = {}
         self._keep = [None] * depth        # keep submitted host tensors alive until their slot is waited on
 

@@ -21,7 +21,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib
-from .guidance import _GuidanceOutputs
+from .guidance import _GuidanceOutputs, _is_sharded, global_ce_mean
 from .loss import _accum_buffer, _device_index, _grad_out_ptr, _new_out, _prep_label, _raw_stream, _require_cuda_f32
 
 
@@ -46,13 +46,8 @@ class _SourceCE(torch.autograd.Function):
                                          aux.data_ptr() if need else None, grad.data_ptr() if need else None, cm_ptr, stream))
         o = _GuidanceOutputs(out, n, c, lay)
         loss = o.loss2
-        if group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            # images sharded over ranks: the mean is over the valid pixels of the WHOLE batch
-            pair = torch.stack([o.ce_sum, o.nvalid.to(torch.float64)])
-            dist.all_reduce(pair, group=group)
-            o.nvalid.copy_(pair[1].round().to(torch.int64))
-            o.ce_sum.copy_(pair[0])
-            loss = (pair[0] / pair[1]).to(torch.float32)
+        if _is_sharded(group):
+            loss = global_ce_mean(o, group)              # the mean is over the valid pixels of the WHOLE batch
         sink.append(o)
         ctx.save_for_backward(lo)
         ctx.keep = (out, aux, grad)

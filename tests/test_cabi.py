@@ -32,7 +32,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.msq_abi_version() == 5
+    assert lib.msq_abi_version() == 6
     assert lib.msq_error_string(0) == b"success"
     for code in (-1, -2, -3, -4):
         assert lib.msq_error_string(code).startswith(b"msq:")
