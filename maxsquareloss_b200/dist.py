@@ -19,6 +19,8 @@ import os
 import torch
 import torch.distributed as dist
 
+from .loss import _raw_stream
+
 
 def image_shard(n_total, rank, world):
     """Contiguous block [lo, hi) of the global batch owned by ``rank`` (cfg 3:
@@ -150,8 +152,9 @@ class StatsComm:
         """Sum the float64 CUDA vector ``buf`` over the ranks, in place, asynchronously w.r.t. the current stream."""
         if not (buf.is_cuda and buf.dtype == torch.float64 and buf.is_contiguous()):
             raise RuntimeError("StatsComm.allreduce needs a contiguous float64 CUDA tensor")
-        stream = torch.cuda.current_stream(buf.device).cuda_stream
-        self._libmod.check(self._lib.msq_comm_allreduce_f64(self._h, buf.data_ptr(), buf.numel(), stream))
+        rc = self._lib.msq_comm_allreduce_f64(self._h, buf.data_ptr(), buf.numel(), _raw_stream(buf.device.index))
+        if rc:
+            self._libmod.check(rc)
 
     def allreduce_u64(self, buf):
         """Sum the int64/uint64 CUDA vector ``buf`` over the ranks, in place (exact): the confusion counts of ``Eval``,
@@ -159,8 +162,9 @@ class StatsComm:
         current stream after it."""
         if not (buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous()):
             raise RuntimeError("StatsComm.allreduce_u64 needs a contiguous int64 CUDA tensor")
-        stream = torch.cuda.current_stream(buf.device).cuda_stream
-        self._libmod.check(self._lib.msq_comm_allreduce_u64(self._h, buf.data_ptr(), buf.numel(), stream))
+        rc = self._lib.msq_comm_allreduce_u64(self._h, buf.data_ptr(), buf.numel(), _raw_stream(buf.device.index))
+        if rc:
+            self._libmod.check(rc)
 
     def allreduce_ptr(self, ptr, count, stream):
         rc = self._lib.msq_comm_allreduce_f64(self._h, ptr, count, stream)
@@ -171,7 +175,7 @@ class StatsComm:
         """Make the current stream wait for the ``allreduce`` issued ``lag`` calls before the most recent one
         (0 = the most recent); no host synchronisation."""
         if stream is None:
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(torch.cuda.current_device())
         rc = self._lib.msq_comm_join(self._h, int(lag), stream)
         if rc:
             self._libmod.check(rc)
