@@ -824,6 +824,10 @@ static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_p
     long long grid = (long long)sms * ctas_per_sm;
     if (g_fused_rows > 0) grid = (p.units + g_fused_rows - 1) / g_fused_rows;
     else if (p.units / grid < 4) grid = p.units / 4;          // tiny problems: at least 4 rows per CTA
+    // the per-thread packed buckets hold a 16-bit pixel count and a 48-bit fixed-point sum per class (q <= 1, entropy
+    // <= ln 32 per pixel): a CTA must not walk more than 2^14 rows (of one image, a fortiori) whatever the knobs say
+    const long long min_grid = (p.units + 16383) / 16384;
+    if (grid < min_grid) grid = min_grid;
     if (grid < 1) grid = 1;
     if (grid > p.units) grid = p.units;
     p.grid = (int)grid;

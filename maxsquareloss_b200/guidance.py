@@ -187,3 +187,41 @@ class MultiLevelTargetLoss(nn.Module):
         self.loss_target = self.lambda_target * res[0]
         self.loss_target_2 = self.lambda_seg * self.lambda_target * res[1]
         return self.loss_target, self.loss_target_2
+
+
+class HardTargetLoss(nn.Module):
+    """``--target_mode hard`` of ``UDATrainer.train_target`` (``tools/solve_gta5.py:149-150,185-199``), fused:
+    ``label = where(max softmax(pred) > threshold, argmax softmax(pred), -1)`` and
+    ``lambda_target * nn.CrossEntropyLoss(ignore_index=-1)(pred, label)`` from the LOW-resolution head logits.
+
+    It is the guidance kernel with both heads bound to the same tensor: ``(P + P) / 2 == P`` exactly, so the ensemble
+    argmax / threshold test of ``msq_multi_fwd`` is this mode's pseudo-label and its head-2 cross-entropy is this loss;
+    ``msq_guidance_bwd`` returns the gradient.  (One softmax more than a dedicated kernel would need; this mode is the
+    reference's self-training baseline, not the path the paper's numbers use.)  CUDA only; no fallback.
+
+    ``forward(pred, out_size)`` returns ``self.loss_target`` (already scaled by ``lambda_target``);
+    ``last_label`` holds the pseudo-label map when ``return_label=True``, ``last_nvalid`` the number of kept pixels."""
+
+    def __init__(self, threshold=0.95, lambda_target=0.1, num_class=19, return_label=False, group=None):
+        super().__init__()
+        self.threshold, self.lambda_target, self.num_class = threshold, lambda_target, num_class
+        self.return_label, self.group = return_label, group
+        self.ignore_index = -1
+        self.last_label = self.last_nvalid = self.loss_target = None
+
+    def forward(self, pred, out_size):
+        if isinstance(pred, (tuple, list)):
+            pred = pred[0]
+        _require_cuda_f32(pred, "head logits")
+        if pred.shape[1] != self.num_class:
+            raise ValueError(f"tensor has {pred.shape[1]} classes but the loss was built with num_class={self.num_class}")
+        if pred.shape[1] > _lib.MAX_CLASSES:
+            raise RuntimeError(f"num_class={pred.shape[1]} exceeds the kernels' limit of {_lib.MAX_CLASSES}")
+        sink = []
+        # head 1 of the kernel is a detached alias (its maximum-squares statistics are not used and get no gradient)
+        res = _MultiLoss.apply(pred.detach(), pred, tuple(out_size), _lib.MODE_MAXSQUARE, 0.0, self.threshold, 0,
+                               self.return_label, self.group, sink)
+        o, label = sink[0]
+        self.last_label, self.last_nvalid = label, o.nvalid
+        self.loss_target = self.lambda_target * res[1]
+        return self.loss_target

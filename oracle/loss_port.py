@@ -130,6 +130,20 @@ def chain_multi(lo1: torch.Tensor, lo2: torch.Tensor, out_hw, num_class: int, ki
                 nvalid=int((label_2 >= 0).sum()), grad1=x1.grad, grad2=x2.grad, hist=hist)
 
 
+def chain_hard(lo: torch.Tensor, out_hw, threshold: float = 0.95, lambda_target: float = 0.1):
+    """``--target_mode hard`` (``tools/solve_gta5.py:149-150,185-199``): pseudo-labels ``argmax(softmax(pred))`` where the
+    maximum probability exceeds ``threshold`` (-1 elsewhere), ``lambda_target * CrossEntropyLoss(ignore_index=-1)``,
+    backward.  Returns dict(loss_target, label, nvalid, grad)."""
+    x = lo.detach().clone().requires_grad_(True)
+    pred, prob = prologue(x, out_hw)
+    label = torch.argmax(prob.detach(), dim=1)                                   # :185-186
+    maxpred, _ = torch.max(prob.detach(), dim=1)                                 # :192
+    label = torch.where(maxpred > threshold, label, torch.ones(1, dtype=torch.long) * -1)      # :195-197
+    loss = lambda_target * F.cross_entropy(pred, label, ignore_index=-1)         # :199
+    loss.backward()
+    return dict(loss_target=loss.detach(), label=label, nvalid=int((label >= 0).sum()), grad=x.grad)
+
+
 def chain_source(logits_lo: torch.Tensor, target: torch.Tensor, num_class: int, grad_scale: float = 1.0):
     """Source-side step (``tools/train_source.py:254,280-283``): upsample -> CrossEntropyLoss(ignore_index=-1)
     -> backward, and the argmax map that goes into ``Eval.add_batch``.

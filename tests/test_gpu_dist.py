@@ -147,3 +147,142 @@ def test_peer_memory_mailboxes_two_ranks():
         for g in got:
             assert np.array_equal(g, ref)                          # two ranks: a + b in rank order == NCCL's sum, bit for bit
     assert np.array_equal(res[0][4][0], res[1][4][0])              # and identical on both ranks
+
+
+def _worker_ce(rank, world, port, q):
+    """The sharded cross-entropy mean on REAL ranks: MultiLevelTargetLoss with the library communicator (exact uint64
+    all-reduce of [ce_fix | nvalid]) and CrossEntropyLoss2d with a torch.distributed group (int64 all_reduce of the same pair)."""
+    sys.path.insert(0, ROOT)
+    import datetime
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
+    import maxsquareloss_b200 as msq
+    from maxsquareloss_b200 import dist as mdist, synth
+    comm = mdist.StatsComm()
+    C, hw, HW, NG = 13, (9, 17), (64, 128), 4
+    a, b = mdist.image_shard(NG, rank, world)
+    lo1 = synth.head_logits(NG, C, hw, 61, 4.0)
+    lo2 = synth.second_head(lo1, 61)
+    y = synth.blocky_labels(NG, HW, C, 62, grid=(4, 8))
+    x1, x2 = lo1[a:b].cuda().requires_grad_(True), lo2[a:b].cuda().requires_grad_(True)
+    crit = msq.IW_MaxSquareloss(-1, C, 0.2)
+    crit.global_batch = NG
+    multi = msq.MultiLevelTargetLoss(crit, threshold=0.9, lambda_target=0.1, lambda_seg=0.1, group=comm)
+    l1, l2 = multi((x1, x2), HW)
+    (l1 + l2).backward()
+    xs = lo1[a:b].cuda().requires_grad_(True)
+    ce = msq.CrossEntropyLoss2d()                       # group=None: the default torch.distributed group
+    ls = ce(xs, y[a:b].cuda())
+    ls.backward()
+    torch.cuda.synchronize()
+    q.put((rank, (a, b), l2.item(), int(multi.last_nvalid.item()), x2.grad.cpu().numpy(), ls.item(), int(ce.last_nvalid.item()),
+           xs.grad.cpu().numpy()))
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_cross_entropy_means_two_ranks():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import maxsquareloss_b200 as msq
+    from maxsquareloss_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_ce, args=(r, 2, 29535, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    C, hw, HW, NG = 13, (9, 17), (64, 128), 4
+    lo1 = synth.head_logits(NG, C, hw, 61, 4.0)
+    lo2 = synth.second_head(lo1, 61)
+    y = synth.blocky_labels(NG, HW, C, 62, grid=(4, 8))
+    x1, x2 = lo1.cuda().requires_grad_(True), lo2.cuda().requires_grad_(True)
+    multi = msq.MultiLevelTargetLoss(msq.IW_MaxSquareloss(-1, C, 0.2), threshold=0.9, lambda_target=0.1, lambda_seg=0.1, group=False)
+    l1, l2 = multi((x1, x2), HW)
+    (l1 + l2).backward()
+    xs = lo1.cuda().requires_grad_(True)
+    ce = msq.CrossEntropyLoss2d(group=False)
+    ls = ce(xs, y.cuda())
+    ls.backward()
+    for rank, (a, b), l2r, nv, g2, lsr, nvs, gs in res:
+        assert nv == int(multi.last_nvalid.item()) and nvs == int(ce.last_nvalid.item())          # global counts: exact
+        assert abs(l2r - l2.item()) <= 1e-6 * abs(l2.item()) and abs(lsr - ls.item()) <= 1e-6 * abs(ls.item())
+        r2, rs = x2.grad[a:b].cpu().numpy(), xs.grad[a:b].cpu().numpy()
+        assert np.abs(g2 - r2).max() <= 1e-5 * np.abs(r2).max()
+        assert np.abs(gs - rs).max() <= 1e-5 * np.abs(rs).max()
+
+
+def _worker_lost(rank, world, port, q):
+    """A peer that stops stepping: the surviving rank's mailbox reductions time out (0.5 s here), its statistics become
+    NaN, the error is reported -- and nothing hangs."""
+    sys.path.insert(0, ROOT)
+    import datetime
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
+    from maxsquareloss_b200 import _lib, dist as mdist, synth
+    lib = _lib.load()
+    C, (h, w), (H, W), N = 19, (33, 65), (257, 513), 2
+    lay = _lib.state_layout(N, C)
+    lo = synth.head_logits(N, C, (h, w), 7 + rank, 4.0).cuda()
+    comm = mdist.StatsComm()
+    if not comm.peer_memory:
+        q.put((rank, "no-ipc"))
+        dist.destroy_process_group()
+        return
+    comm.set_timeout(0.5)
+    accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda")
+    aux = torch.empty(lib.msq_fused_aux_bytes(N, H, W), dtype=torch.uint8, device="cuda")
+    grad = torch.empty_like(lo)
+    stream = torch.cuda.current_stream().cuda_stream
+    steps = 6 if rank == 0 else 3                        # rank 1 "dies" after three steps
+    codes = []
+    t0 = time.perf_counter()
+    for i in range(steps):
+        codes.append(lib.msq_fused_fwd_bwd(_lib.MODE_IW, lo.data_ptr(), N, C, h, w, H, W, 0.2, N * world, accum.data_ptr(),
+                                           out.data_ptr(), aux.data_ptr(), None, 0.1, grad.data_ptr(), comm._h, 0, stream))
+        torch.cuda.synchronize()
+    rc_join = lib.msq_comm_join(comm._h, 0, stream) if rank == 0 else 0        # the dead rank does not even flush
+    torch.cuda.synchronize()
+    took = time.perf_counter() - t0
+    red = comm.result(1 + C, lag=0).cpu().numpy() if rank == 0 else None
+    if rank == 0:
+        codes.append(lib.msq_comm_join(comm._h, 0, stream))
+    q.put((rank, codes, rc_join, comm.errors(), took, red))
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_lost_peer_times_out_and_is_reported():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from maxsquareloss_b200 import _lib
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_lost, args=(r, 2, 29536, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    if res[0][1] == "no-ipc":
+        pytest.skip("CUDA IPC peer mapping is not available on this box")
+    _, codes, rc_join, err, took, red = res[0]
+    assert took < 30.0                                              # bounded: a few 0.5 s time-outs, never a hang
+    assert err != 0                                                 # the loss is recorded ...
+    assert _lib.load().msq_error_string(-6).startswith(b"msq:")
+    assert -6 in codes + [rc_join]                                  # ... and returned (MSQ_E_PEER) by a later call
+    assert np.isnan(red).any()                                      # the vector that needed the dead rank is NaN, not garbage
+    assert res[1][3] == 0                                           # the rank that stopped saw no loss itself
