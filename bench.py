@@ -527,6 +527,7 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.skip_secondary:        # per-GPU numbers: reported by the N = 1 run only
         kernels += secondary_kernels(lib, _lib, synth, dev, stream, hbm_peak, kit)
         extra["maxsquare"] = maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, aux_ptrs, acc_ptr, go_ptr, n_norm, stream, kit)
+        extra["marginal_image"] = marginal_image_cost(lib, _lib, dev, stream, kit)
         extra["next_rows"] = next_rows(lib, _lib, synth, dev, stream, kit)
         extra["torch_cuda_eager_baseline"] = torch_eager_gpu(dev)
     dom = max(kernels[:2], key=lambda k: k["ms"])
@@ -1122,6 +1123,38 @@ def torch_eager_gpu(dev, iters=20):
     t = (time.perf_counter() - t0) / iters
     return {"value": PX_PER_STEP / t / 1e9, "unit": UNIT, "ms_per_step": t * 1e3,
             "what": "reference op chain (oracle port) on torch CUDA eager, same GPU, device-resident input"}
+
+
+def marginal_image_cost(lib, _lib, dev, stream, kit):
+    """us per step of the one-call fused IW step at 1, 2 and 4 images per GPU (cold inputs) and the slope between them: what
+    one more image costs against the fixed part of a step (launches, one-wave ramp-up / tail, per-CTA set-up)."""
+    h, w = HW_LO
+    H, W = HW_OUT
+    out = {}
+    for n in (1, 2, 4):
+        pool = max(8, min(POOL, int(170e6 // (4 * n * C * h * w)) + 1))
+        lo = torch.randn(pool, n, C, h, w, device=dev) * 5.0
+        gr = torch.empty_like(lo)
+        lay = _lib.state_layout(n, C)
+        accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device=dev)
+        outs = torch.empty(8, lay.out_bytes, dtype=torch.uint8, device=dev)
+        nb = lib.msq_fused_aux_bytes(n, H, W)
+        naux = max(2, min(10, int(170e6 // nb) + 1))
+        aux = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(naux)]
+
+        def step(i):
+            j = i % pool
+            rc = lib.msq_fused_fwd_bwd(_lib.MODE_IW, lo[j].data_ptr(), n, C, h, w, H, W, RATIO, 0, accum.data_ptr(),
+                                       outs[i % 8].data_ptr(), aux[i % naux].data_ptr(), None, LAMBDA_TARGET, gr[j].data_ptr(),
+                                       None, 0, stream)
+            if rc:
+                _lib.check(rc)
+        out[n] = time_loop(step, max(kit, 300), 50) * 1e3
+        del lo, gr, aux
+    return {"us_per_step_by_images": {str(k): v for k, v in out.items()},
+            "marginal_us_per_image": (out[4] - out[1]) / 3.0, "fixed_us_per_step": out[1] - (out[4] - out[1]) / 3.0,
+            "what": "one-call fused IW step (forward + finalise + backward), cold inputs; marginal = (t4 - t1) / 3, "
+                    "fixed = t1 - marginal"}
 
 
 def maxsquare_variant(lib, _lib, lo_ptrs, gr_ptrs, out_ptrs, aux_ptrs, acc_ptr, go_ptr, n_norm, stream, kit):

@@ -87,6 +87,11 @@ class Eval:
         self.defer = int(defer)
         self._queue = []                 # deferred (gt, pred, gt._version, pred._version)
         self._per_image = []             # device blocks (k, C*C) int64 of add_batch_per_image, in call order
+        # the deferred queue's pointer table is filled as the calls come in, so that a flush is ONE library call
+        kq = max(self.defer, 1)
+        self._q_gt, self._q_pr = (ctypes.c_void_p * kq)(), (ctypes.c_void_p * kq)()
+        self._q_np = (ctypes.c_int64 * kq)()
+        self._multi = _lib.load().msq_confusion_i64_multi
 
     # ------------------------------------------------------------------ accumulate
     def add_batch(self, gt_image, pre_image):
@@ -96,14 +101,17 @@ class Eval:
                 pre_image.dim() == np.ndim(gt_image) + 1:
             return self.add_batch_logits(gt_image, pre_image)
         # assert the size of two images are same (utils/eval.py:119)
-        assert tuple(gt_image.shape) == tuple(pre_image.shape)
+        assert gt_image.shape == pre_image.shape
         host_call = not (isinstance(gt_image, torch.Tensor) and gt_image.is_cuda and
                          isinstance(pre_image, torch.Tensor) and pre_image.is_cuda)
         gt = _to_device_labels(gt_image, self.device, self.num_class, True)
         pr = _to_device_labels(pre_image, self.device, self.num_class, False)
         if self.defer > 0 and not host_call:
-            self._queue.append((gt, pr, gt._version, pr._version))
-            if len(self._queue) >= self.defer:
+            q = self._queue
+            k = len(q)
+            self._q_gt[k], self._q_pr[k], self._q_np[k] = gt.data_ptr(), pr.data_ptr(), gt.numel()
+            q.append((gt, pr, gt._version, pr._version))
+            if k + 1 >= self.defer:
                 self._flush_queue()
             return
         rc = self._call(gt.data_ptr(), pr.data_ptr(), gt.numel(), self.num_class, self._cm_ptr, self._err_ptr,
@@ -134,7 +142,11 @@ class Eval:
             if gt._version != vg or pr._version != vp:
                 raise RuntimeError("Eval(defer=K): a tensor handed to add_batch was modified in place before the queued "
                                    "launch ran; pass fresh tensors or read a metric / call flush() first")
-        self._launch_multi(q, self._cm_ptr, 0, None)
+        rc = self._multi(self._q_gt, self._q_pr, self._q_np, len(q), self.num_class, self._cm_ptr, 0, None, self._err_ptr,
+                         _raw_stream(self._dev_index))            # the table was filled as the calls came in
+        if rc:
+            _lib.check(rc)
+        self._pending = True
 
     def flush(self):
         """Run the queued ``add_batch`` calls now (``defer`` > 0); no host synchronisation."""
