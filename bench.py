@@ -761,10 +761,10 @@ def cpu_eval_check(ch):
 def cfg3_leg(lib, _lib, synth, mdist, comm, dev, stream, rank, world, dist, kit):
     """BASELINE config 3: MaxSquare+IW+Multi (tools/solve_gta5.py:178-218 with --multi): IW-MaxSquare on head 1 +
     self-produced guidance cross-entropy on head 2, GLOBAL batch 8 strong-sharded over the ranks (8/G images each).
-    Per step and rank: msq_multi_fwd (both heads, one kernel + finalisation), the exact uint64 all-reduce of the
-    [cross-entropy sum | valid-pixel count] pair forked right after it (the head-2 backward divides by the GLOBAL count),
-    msq_fused_bwd for head 1 (overlaps the collective), join, msq_guidance_bwd for head 2; the [loss | hist] vector of
-    head 1 is all-reduced as well.  check: the all-reduced integers against ONE GPU computing all 8 images."""
+    Per step and rank: msq_multi_fwd (both heads, one kernel + finalisation), the exact integer sum of the
+    [cross-entropy sum | valid-pixel count] pair begun right after it (the head-2 backward divides by the GLOBAL count),
+    msq_fused_bwd for head 1 (the pairs cross NVLink meanwhile), the sum's end, msq_guidance_bwd for head 2; the
+    [loss | hist] vector of head 1 is all-reduced as well (NCCL, side stream).  check: the all-reduced integers against ONE GPU computing all 8 images."""
     NG, thr = 8, 0.95
     if NG % world:
         return {"skipped": f"global batch {NG} does not divide over {world} ranks"}
@@ -794,14 +794,14 @@ def cfg3_leg(lib, _lib, synth, mdist, comm, dev, stream, rank, world, dist, kit)
                                acc.data_ptr(), o.data_ptr(), a1.data_ptr(), a2.data_ptr(), gr1.data_ptr(), gr2.data_ptr(), None, stream)
         if rc:
             _lib.check(rc)
-        if sharded:
-            _lib.check(lib.msq_comm_allreduce_u64(comm_h, o.data_ptr() + lay_of(n).ce_fix_out_off, 2, stream))
+        if sharded:         # push this rank's [ce_fix | nvalid] into every rank's mailbox (NVLink) ...
+            _lib.check(lib.msq_comm_sum_u64_begin(comm_h, o.data_ptr() + lay_of(n).ce_fix_out_off, 2, stream))
         rc = lib.msq_fused_bwd(_lib.MODE_IW, l1.data_ptr(), n, C, h, w, H, W, NG, o.data_ptr(), a1.data_ptr(), go.data_ptr(),
                                gr1.data_ptr(), 1, stream)
         if rc:
             _lib.check(rc)
-        if sharded:
-            _lib.check(lib.msq_comm_join(comm_h, 0, stream))
+        if sharded:         # ... and sum the pairs of all ranks (arrived during the head-1 backward) in place
+            _lib.check(lib.msq_comm_sum_u64_end(comm_h, o.data_ptr() + lay_of(n).ce_fix_out_off, 2, stream))
         rc = lib.msq_guidance_bwd(l2.data_ptr(), n, C, h, w, H, W, o.data_ptr(), a2.data_ptr(), go2.data_ptr(), gr2.data_ptr(), 1, stream)
         if rc:
             _lib.check(rc)
@@ -837,9 +837,11 @@ def cfg3_leg(lib, _lib, synth, mdist, comm, dev, stream, rank, world, dist, kit)
     res = {"what": "cfg3 MaxSquare+IW+Multi step (tools/solve_gta5.py:178-218 --multi): IW-MaxSquare head 1 + guidance CE head 2, "
                    f"forward + both backwards, global batch {NG} strong-sharded over {world} rank(s) ({nl} images each), "
                    "65x129 -> 512x1024, thr 0.95, lambda 0.1/0.1",
-           "scaling": "strong", "us_per_step": ms * 1e3, "value": px / ms / 1e6, "unit": UNIT, "launches_per_step": 4,
-           "exchange": None if not sharded else "exact uint64 ncclAllReduce of [ce_fix | nvalid] between forward and head-2 backward "
-                                                "(overlapped with the head-1 backward) + fp64 ncclAllReduce of [loss | hist], library communicator"}
+           "scaling": "strong", "us_per_step": ms * 1e3, "value": px / ms / 1e6, "unit": UNIT, "launches_per_step": 4 + (2 if sharded and comm.peer_memory else 0),
+           "exchange": None if not sharded else ("same-step integer sum of [ce_fix | nvalid] over the NVLink peer-memory mailboxes "
+                                                 "(msq_comm_sum_u64_begin after the forward, _end before the head-2 backward: two "
+                                                 "32-thread kernels)" if comm.peer_memory else "ncclAllReduce(uint64) of [ce_fix | nvalid] "
+                                                 "between forward and head-2 backward") + " + fp64 ncclAllReduce of [loss | hist] on the side stream"}
     # ---- parity of the sharded step against ONE GPU doing all 8 images (pool entry 0)
     step(0)
     if sharded:

@@ -317,6 +317,13 @@ int msq_comm_allreduce_f64(msq_comm* comm, double* buf /* device, in place */, i
 /* the same for the path's INTEGER results (confusion counts of Eval, utils/eval.py:121; the adjacent
  * [ce_fix_out | nvalid_out] pair of the cross-entropy rows): uint64 words, exact whatever the order of the sum */
 int msq_comm_allreduce_u64(msq_comm* comm, unsigned long long* buf /* device, in place */, int count, msq_stream_t stream);
+/* The same sum for <= 2 words that the SAME step consumes (the [ce_fix_out | nvalid_out] pair: msq_guidance_bwd divides by the
+ * global count): _begin right after the forward, independent work on the stream, _end right before the consumer.  Mailboxes
+ * open: two 32-thread kernels, the words cross NVLink as 16-byte stores and a spinning warp sums them as integers (a few us
+ * instead of a ~25 us collective launch); else one ncclAllReduce(uint64) on the side stream joined by _end.  One exchange in
+ * flight per communicator; dst may equal src; every rank calls both, in the same order as its other mailbox steps. */
+int msq_comm_sum_u64_begin(msq_comm* comm, const unsigned long long* src /* device */, int count, msq_stream_t stream);
+int msq_comm_sum_u64_end(msq_comm* comm, unsigned long long* dst /* device */, int count, msq_stream_t stream);
 int msq_comm_join(msq_comm* comm, int lag /* 0 = most recent all-reduce, k = k calls earlier (< 8) */, msq_stream_t stream);
 void msq_comm_destroy(msq_comm* comm);
 

@@ -17,7 +17,7 @@ MODE_IW = 1
 #: every symbol include/msq_b200.h declares
 SYMBOLS = ("msq_abi_version", "msq_launch_count", "msq_fused_aux_bytes", "msq_error_string", "msq_state_layout_get", "msq_prob_fwd", "msq_prob_bwd",
            "msq_fused_fwd", "msq_fused_bwd", "msq_entropy_fwd", "msq_entropy_bwd", "msq_multi_fwd", "msq_guidance_bwd", "msq_source_ce_fwd", "msq_confusion_i64", "msq_confusion_i64_multi", "msq_confusion_per_image_logits_f32", "msq_softce_fwd", "msq_softce_bwd", "msq_confusion_logits_f32", "msq_confusion_flip_f32", "msq_tune_set",
-           "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_allreduce_u64", "msq_comm_join", "msq_comm_destroy",
+           "msq_fused_fwd_bwd", "msq_comm_unique_id", "msq_comm_create", "msq_comm_allreduce_f64", "msq_comm_allreduce_u64", "msq_comm_sum_u64_begin", "msq_comm_sum_u64_end", "msq_comm_join", "msq_comm_destroy",
            "msq_comm_box_export", "msq_comm_box_open", "msq_comm_box_enable", "msq_comm_box_active", "msq_comm_box_errors", "msq_comm_box_timeout", "msq_comm_result",
            "msq_pipe_create", "msq_pipe_shard", "msq_pipe_submit", "msq_pipe_wait", "msq_pipe_drain", "msq_pipe_destroy")
 
@@ -113,6 +113,10 @@ def load():
         lib.msq_comm_allreduce_f64.argtypes = [vp, vp, i32, vp]
         lib.msq_comm_allreduce_u64.restype = i32
         lib.msq_comm_allreduce_u64.argtypes = [vp, vp, i32, vp]
+        lib.msq_comm_sum_u64_begin.restype = i32
+        lib.msq_comm_sum_u64_begin.argtypes = [vp, vp, i32, vp]
+        lib.msq_comm_sum_u64_end.restype = i32
+        lib.msq_comm_sum_u64_end.argtypes = [vp, vp, i32, vp]
         lib.msq_comm_join.restype = i32
         lib.msq_comm_join.argtypes = [vp, i32, vp]
         lib.msq_comm_box_export.restype = i32

@@ -78,6 +78,10 @@ struct msq_comm {
     msq::PeerBoxStatic* box_static;       // device copy of {world, rank, err, timeout, peers}
     msq::PeerBoxStatic box_static_host;
     bool box_mapped, box_ready;           // peers mapped / mailbox path switched on (msq_comm_box_enable)
+    // ---- same-step sum of a few uint64 words (msq_comm_sum_u64_begin / _end) ----
+    unsigned u64_seq;                     // exchanges begun (mailbox cells kBoxCount-2.. carry them: flags count independently)
+    int u64_pending;                      // words of the exchange begun and not yet ended (0: none)
+    unsigned long long* u64_buf;          // NCCL path: [kU64Ring][kU64Max] staging words (cudaMalloc)
 };
 
 namespace {
@@ -90,6 +94,48 @@ __global__ void __launch_bounds__(32) box_flush_kernel(const msq::PeerBox box, u
     msq::box_exchange(box, (int)threadIdx.x);
     __syncwarp();
     if (last_out) msq::box_reduce(box.st, last_seq, last_count, last_out, (int)threadIdx.x);
+}
+
+constexpr int kU64Max = 2, kU64Ring = 4;
+constexpr int kU64Cell = msq::kBoxCount - kU64Max;       // mailbox cells 38, 39: never used by a statistics vector (<= 33 doubles)
+
+// Same-step exchange over the mailboxes, split in two tiny kernels so that the caller can put independent work between them:
+// push this rank's words into every rank's ring ...
+__global__ void __launch_bounds__(32) u64_push_kernel(const msq::PeerBoxStatic* st, unsigned seq, const unsigned long long* src, int count) {
+    const int lane = (int)threadIdx.x;
+    if (lane >= count) return;
+    const double v = __longlong_as_double((long long)src[lane]);          // the cell carries 64 raw bits
+    for (int p = 0; p < st->world; ++p) msq::ll_store(msq::box_cell(st->peer[p], seq, st->rank, kU64Cell + lane), v, seq);
+}
+// ... and sum, as INTEGERS, what all ranks pushed for the same sequence number (spins until they have; time-out as box_reduce)
+__global__ void __launch_bounds__(32) u64_reduce_kernel(const msq::PeerBoxStatic* st, unsigned seq, unsigned long long* dst, int count) {
+    const int lane = (int)threadIdx.x;
+    uint4* mine = st->peer[st->rank];
+    const unsigned long long limit = st->timeout_ns;
+    unsigned long long t0 = 0ull, sum = 0ull;
+    bool lost = false;
+    if (lane < count) {
+        for (int p = 0; p < st->world; ++p) {
+            const uint4* cell = msq::box_cell(mine, seq, p, kU64Cell + lane);
+            double v = 0.0;
+            unsigned spins = 0;
+            while (!lost && !msq::ll_load(cell, seq, v)) {
+                if ((++spins & 255u) == 0u) {
+                    const unsigned long long now = msq::global_ns();
+                    if (t0 == 0ull) t0 = now;
+                    else if (now - t0 > limit) lost = true;
+                }
+                __nanosleep(64);
+            }
+            sum += lost ? 0ull : (unsigned long long)__double_as_longlong(v);
+        }
+        dst[lane] = lost ? 0ull : sum;                                    // a lost peer: 0 (a zero count divides to NaN downstream)
+    }
+    if (__any_sync(0xffffffffu, lost) && lane == 0) {
+        volatile unsigned* e = st->err;
+        e[0] = e[0] | 1u;
+        e[1] = e[1] + 1u;
+    }
 }
 
 inline double* vec_slot(const msq_comm* c, unsigned seq) { return c->box_vec + (size_t)(seq % msq::kBoxSlots) * msq::kBoxCount; }
@@ -132,6 +178,9 @@ extern "C" int msq_comm_create(const void* id128, int world, int rank, msq_comm*
     cudaMemset(c->ring, 0, 2 * kRingDoubles * sizeof(double));
     c->box_vec = c->ring;
     c->box_red = c->ring + kRingDoubles;
+    if ((e = cudaMalloc((void**)&c->u64_buf, sizeof(unsigned long long) * kU64Ring * kU64Max)) != cudaSuccess) {
+        cudaStreamDestroy(c->side); cudaFree(c->ring); delete c; return (int)e;
+    }
     cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
     for (int i = 0; i < kRing; ++i) cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
     if (nccl().comm_init_rank(&c->comm, world, id, rank) != 0) {
@@ -216,6 +265,49 @@ extern "C" int msq_comm_result(msq_comm* c, int lag, double* dst, int count, msq
         if (e != cudaSuccess) return (int)e;
     }
     return (int)cudaMemcpyAsync(dst, red_slot(c, k), (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, s);
+}
+
+// Sum over the ranks of `count` (<= 2) uint64 words, available in the SAME step -- the adjacent [ce_fix_out | nvalid_out] pair of
+// the cross-entropy rows, which the head-2 / source backward divides by (msq_guidance_bwd): begin right after the forward,
+// put independent work (the head-1 backward) on the stream, end right before the consumer.  With the mailboxes open: two
+// 32-thread kernels, the words cross NVLink as 16-byte stores and are summed as integers by a spinning warp (a few us,
+// against ~25 us for launching a collective); otherwise: one ncclAllReduce(uint64) on the side stream, joined by _end.
+// One exchange may be in flight per communicator.  dst may equal src.
+extern "C" int msq_comm_sum_u64_begin(msq_comm* c, const unsigned long long* src, int count, msq_stream_t stream) {
+    if (!c || !src || count < 1 || count > kU64Max || c->u64_pending) return MSQ_E_BADARG;
+    if (((uintptr_t)src) & 7u) return MSQ_E_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    c->u64_seq++;
+    c->u64_pending = count;
+    if (c->world == 1) return 0;
+    if (c->box_ready) {
+        u64_push_kernel<<<1, 32, 0, s>>>(c->box_static, c->u64_seq, src, count);
+        MSQ_CHECK_LAUNCH();
+        msq::count_launch();
+        return 0;
+    }
+    unsigned long long* stage = c->u64_buf + (size_t)(c->u64_seq % kU64Ring) * kU64Max;
+    const cudaError_t e = cudaMemcpyAsync(stage, src, sizeof(unsigned long long) * count, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    return comm_allreduce(c, stage, count, kNcclUint64, stream);
+}
+
+extern "C" int msq_comm_sum_u64_end(msq_comm* c, unsigned long long* dst, int count, msq_stream_t stream) {
+    if (!c || !dst || count != c->u64_pending || count < 1) return MSQ_E_BADARG;
+    if (((uintptr_t)dst) & 7u) return MSQ_E_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    c->u64_pending = 0;
+    if (c->world == 1) return 0;                     // the caller's words are the sum
+    if (c->box_ready) {
+        u64_reduce_kernel<<<1, 32, 0, s>>>(c->box_static, c->u64_seq, dst, count);
+        MSQ_CHECK_LAUNCH();
+        msq::count_launch();
+        return peer_error(c);
+    }
+    const cudaError_t e = cudaStreamWaitEvent(s, c->done[(c->issued - 1) % kRing], 0);
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long* stage = c->u64_buf + (size_t)(c->u64_seq % kU64Ring) * kU64Max;
+    return (int)cudaMemcpyAsync(dst, stage, sizeof(unsigned long long) * count, cudaMemcpyDeviceToDevice, s);
 }
 
 // ---- peer-memory mailboxes -------------------------------------------------------------------------------
@@ -317,6 +409,7 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
     }
     if (c->err_host) cudaFreeHost(c->err_host);
     if (c->ring) cudaFree(c->ring);
+    if (c->u64_buf) cudaFree(c->u64_buf);
     if (c->comm) nccl().comm_destroy(c->comm);
     cudaEventDestroy(c->fork);
     for (int i = 0; i < kRing; ++i) cudaEventDestroy(c->done[i]);

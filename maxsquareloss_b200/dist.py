@@ -166,6 +166,21 @@ class StatsComm:
         if rc:
             self._libmod.check(rc)
 
+    def sum_u64_begin(self, buf):
+        """Start the same-step sum over the ranks of the <= 2 int64 words of ``buf`` (mailboxes: NVLink stores from a 32-thread
+        kernel; else ncclAllReduce on the side stream).  Put independent work on the stream, then ``sum_u64_end``."""
+        if not (buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous() and buf.numel() <= 2):
+            raise RuntimeError("StatsComm.sum_u64_begin needs a contiguous int64 CUDA tensor of at most 2 elements")
+        rc = self._lib.msq_comm_sum_u64_begin(self._h, buf.data_ptr(), buf.numel(), _raw_stream(buf.device.index))
+        if rc:
+            self._libmod.check(rc)
+
+    def sum_u64_end(self, buf):
+        """Finish it: after this call (in stream order) ``buf`` holds the global sums."""
+        rc = self._lib.msq_comm_sum_u64_end(self._h, buf.data_ptr(), buf.numel(), _raw_stream(buf.device.index))
+        if rc:
+            self._libmod.check(rc)
+
     def allreduce_ptr(self, ptr, count, stream):
         rc = self._lib.msq_comm_allreduce_f64(self._h, ptr, count, stream)
         if rc:

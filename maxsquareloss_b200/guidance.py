@@ -61,9 +61,9 @@ def global_ce_mean(o, group):
     ``group``: a ``torch.distributed`` group (ProcessGroupNCCL) or a ``dist.StatsComm`` (the library's own communicator:
     one ``ncclAllReduce`` on a side stream, ~3 us of host time).  Returns the global mean as a 0-dim float32 tensor."""
     pair = o.ce_pair
-    if hasattr(group, "allreduce_u64"):
-        group.allreduce_u64(pair)
-        group.join()
+    if hasattr(group, "sum_u64_begin"):                      # dist.StatsComm: NVLink mailboxes (or the library's ncclAllReduce)
+        group.sum_u64_begin(pair)
+        group.sum_u64_end(pair)
     else:
         dist.all_reduce(pair, group=group)
     ce = pair[0].to(torch.float64) * (2.0 ** -32)

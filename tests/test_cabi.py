@@ -134,6 +134,9 @@ def test_comm_entry_points_reject_bad_arguments(lib):
     assert lib.msq_comm_create(b"\0" * 128, 2, 5, ctypes.byref(h)) == -1
     assert lib.msq_comm_allreduce_f64(None, None, 1, None) == -1
     assert lib.msq_comm_join(None, 0, None) == -1
+    assert lib.msq_comm_allreduce_u64(None, None, 1, None) == -1
+    assert lib.msq_comm_sum_u64_begin(None, None, 2, None) == -1
+    assert lib.msq_comm_sum_u64_end(None, None, 2, None) == -1
     assert lib.msq_error_string(-5).startswith(b"msq:")
 
 
