@@ -9,7 +9,7 @@
 namespace msq {
 
 #ifndef MSQ_TW
-#define MSQ_TW 128                              // A/B builds: -DMSQ_TW=64 (with MSQ_FWD_MINB / MSQ_BWD_MINB = 8)
+#define MSQ_TW 128                              // measured: 64-thread CTAs (8 per SM) lose at batch 1-2 (40.4 vs 33.9 us), profiles/r02_ab_rejected.txt
 #endif
 constexpr int kTW = MSQ_TW;                     // output columns (= threads) per CTA
 static_assert(kTW % 32 == 0 && kTW >= 32 && kTW <= 256, "kTW: whole warps, at least MSQ_MAX_CLASSES threads");
@@ -237,14 +237,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Experimental (A/B builds, -DMSQ_BWD_CACHE_RING=S, default 0 = off): the backward fetches the forward's 16 B/pixel
-// statistics cache S rows ahead through a per-thread shared-memory ring filled with cp.async, instead of one row ahead
-// through a register: hides the L2 / HBM latency of that stream (long_scoreboard was 1.46 of ~7 stall cycles per issue in the
-// ncu capture) and frees the four prefetch registers.  Every thread reads only the slots it filled itself: no barrier.
-#ifndef MSQ_BWD_CACHE_RING
-#define MSQ_BWD_CACHE_RING 0
-#endif
 
 // Class pitch of the shared-memory tile: the tile is stored channel-LAST, [row][col][cpd(CT)],
 // so that the C logits of one low-res cell are contiguous and a thread fetches them with
@@ -511,9 +503,6 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     int* s_j0 = (int*)(s_lx1 + kTW);                         // [kTW]
     int* s_j1 = s_j0 + kTW;                                  // [kTW]
     int* s_rng = s_j1 + kTW;                                 // [4][ncp]: start0,end0,start1,end1
-#if MSQ_BWD_CACHE_RING
-    float4* s_ring = (float4*)((((uintptr_t)(s_rng + 4 * g.ncp)) + 15u) & ~(uintptr_t)15u);      // [MSQ_BWD_CACHE_RING][kTW]
-#endif
     __shared__ float s_coef[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x;
     const bool fastx = g.fastx != 0;
@@ -638,37 +627,15 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         // cached statistics of the next row are fetched while the current row is computed
         const float4* axp = CACHED ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
         float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-#if MSQ_BWD_CACHE_RING
-        if (CACHED) {
-#pragma unroll
-            for (int s = 0; s < MSQ_BWD_CACHE_RING; ++s) {
-                if (sp.ys + s < sp.ye) cp_async16(&s_ring[s * kTW + tid], axp + (long long)s * g.W);
-                cp_async_commit();                           // one group per row, empty past the end: uniform counting
-            }
-        }
-#else
         if (CACHED) nx = __ldg(axp);
-#endif
         for (int y = sp.ys; y < sp.ye; ++y) {
             int y0, y1;
             float ly0, ly1;
             row_params(s_rows, g, use_tab, sp.ys, y, y0, y1, ly0, ly1);
-#if MSQ_BWD_CACHE_RING
-            if (CACHED) {
-                cp_async_wait<MSQ_BWD_CACHE_RING - 1>();     // the group of row y has landed
-                float4* slot = &s_ring[((y - sp.ys) % MSQ_BWD_CACHE_RING) * kTW + tid];
-                nx = *slot;
-                asm volatile("" :: "f"(nx.x), "f"(nx.y), "f"(nx.z), "f"(nx.w) : "memory");      // read before the refill is issued
-                if (y + MSQ_BWD_CACHE_RING < sp.ye) cp_async16(slot, axp + (long long)(y - sp.ys + MSQ_BWD_CACHE_RING) * g.W);
-                cp_async_commit();
-            }
-#endif
             const float c_m = nx.x, c_qs = nx.y, c_is2 = nx.z;
             const float nx_prev_z = nx.z;                    // GUIDE: label_2 bits
             const int c_k = __float_as_int(nx.w);
-#if !MSQ_BWD_CACHE_RING
             if (CACHED && y + 1 < sp.ye) { axp += g.W; nx = __ldg(axp); }
-#endif
             if (y0 != ra) {
                 if (ra >= 0) flush_row(ra, dHa);
                 if (y0 == rb) {
@@ -910,8 +877,7 @@ static inline size_t fwd_smem(const FusedGeo& g, bool iw, int ct) {
 static inline size_t bwd_smem(const FusedGeo& g, int ct) {
     return row_tab_bytes(g) + tile_bytes(g, ct) +
            ((size_t)(kTW + kRun) * (cpd(ct) + 2) + (size_t)g.ncp * 2 * kRun + 2 * kTW) * sizeof(float) +
-           (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int) +
-           (MSQ_BWD_CACHE_RING ? 16 + (size_t)MSQ_BWD_CACHE_RING * kTW * sizeof(float4) : 0);
+           (2 * kTW + 4 * (size_t)g.ncp) * sizeof(int);
 }
 
 

@@ -1,4 +1,4 @@
-"""A/B of build variants of the fused kernels (development aid for the next round).
+"""A/B of build variants of the fused kernels (development aid; round-2 results: profiles/r02_ab_rejected.txt).
 
     python scripts/ab_variants.py build      # here, on the CPU: nvcc cross-compiles every variant into lib/variants/
     python scripts/ab_variants.py run        # on the B200 (gpurun): correctness spot check + fwd / bwd / step times per variant
@@ -11,10 +11,7 @@ sys.path.insert(0, ROOT)
 VARDIR = os.path.join(ROOT, "maxsquareloss_b200", "lib", "variants")
 VARIANTS = {
     "base": (),
-    "tw64": ("MSQ_TW=64", "MSQ_FWD_MINB=8", "MSQ_BWD_MINB=8", "MSQ_MULTI_MINB=4", "MSQ_SRC_MINB=8"),
-    "ring2": ("MSQ_BWD_CACHE_RING=2",),
-    "ring4": ("MSQ_BWD_CACHE_RING=4",),
-    "tw64_ring4": ("MSQ_TW=64", "MSQ_FWD_MINB=8", "MSQ_BWD_MINB=8", "MSQ_MULTI_MINB=4", "MSQ_SRC_MINB=8", "MSQ_BWD_CACHE_RING=4"),
+    "tw64": ("MSQ_TW=64", "MSQ_FWD_MINB=8", "MSQ_BWD_MINB=8", "MSQ_MULTI_MINB=4", "MSQ_SRC_MINB=8"),       # measured in round 2: loses at batch 1-2
 }
 
 
