@@ -145,6 +145,36 @@ __device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+
+// Development aid (-DMSQ_TRACE=1, scripts/trace_step.py): thread 0 of every CTA stamps %globaltimer at a few points of the
+// step's kernels into a per-translation-unit device array, read back with msq_debug_trace_*().  Off in the product build.
+#ifndef MSQ_TRACE
+#define MSQ_TRACE 0
+#endif
+#if MSQ_TRACE
+constexpr int kTraceCtas = 1024, kTracePts = 8;
+static __device__ unsigned long long g_trace[4 * kTraceCtas * kTracePts];      // [kernel * 2 + step parity][CTA][point]
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned smid() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
+#define MSQ_TRACE_PT(kid, i)                                                                           \
+    do {                                                                                               \
+        if (threadIdx.x == 0 && blockIdx.x < kTraceCtas) {                                             \
+            g_trace[((kid) * kTraceCtas + blockIdx.x) * kTracePts + (i)] = gtime();                    \
+            if ((i) == 0) g_trace[((kid) * kTraceCtas + blockIdx.x) * kTracePts + 7] = smid();         \
+        }                                                                                              \
+    } while (0)
+#else
+#define MSQ_TRACE_PT(kid, i) do {} while (0)
+#endif
+
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
 // serialisation attribute may start while its predecessor is still running; it must call
 // pdl_wait() before touching anything the predecessor (transitively: any earlier kernel)
@@ -190,8 +220,10 @@ __device__ __forceinline__ float iw_weight(float hist, float total, float r32, f
 // Finalisation (the body of api.cu's finalize_kernel, also run by the last CTA of the fused step kernel):
 // one warp per image, one lane per class (C <= 32)
 // (any block size that is a multiple of 32, up to 256 threads; called by every thread of ONE CTA)
+// `defer_clean`: leave the accumulators as they are (finalize_clean() zeroes them later): the one-call step runs this body
+// while its backward kernel is still reading the class histograms.
 __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                                              unsigned long long kept_dense, int multi, int loss_kind) {
+                                              unsigned long long kept_dense, int multi, int loss_kind, bool defer_clean = false) {
     __shared__ double s_red[8];
     __shared__ unsigned long long s_cls[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
@@ -201,7 +233,10 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
     if (tid == 0) { kept_ld = __ldcg(st.kept); flags_ld = __ldcg(st.flags); }
     // multi-level guidance: cross-entropy sum and valid-pixel count, one replica per lane of warp 0
     unsigned long long ce_ld = 0ull, nv_ld = 0ull;
-    if (multi && tid < kRep) { ce_ld = st.ce[tid]; nv_ld = st.nvalid[tid]; st.ce[tid] = 0ull; st.nvalid[tid] = 0ull; }
+    if (multi && tid < kRep) {
+        ce_ld = st.ce[tid]; nv_ld = st.nvalid[tid];
+        if (!defer_clean) { st.ce[tid] = 0ull; st.nvalid[tid] = 0ull; }
+    }
     if (tid < MSQ_MAX_CLASSES) s_cls[tid] = 0ull;
     __syncthreads();
     const int nc = n * C;
@@ -213,17 +248,30 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
         unsigned long long sq = 0ull;
         double sd = 0.0;
         if (lane < C) {
+            // all 2 x kRep loads are issued before the first use: ONE L2 round trip (the compiler used to start summing after
+            // the first 20 and paid a second one: 1.4 us of this kernel's 2.9 us, profiles/r02_trace_step.txt)
+            unsigned hv[kRep];
+            unsigned long long sv[kRep];
 #pragma unroll
-            for (int r = 0; r < kRep; ++r) {          // independent loads: one latency
-                hcnt += __ldcg(&st.hist[r * nc + idx]);          // L2: other CTAs' atomics (fused step kernel)
-                const unsigned long long v = __ldcg(&st.sumsq[r * nc + idx]);
-                if (loss_kind == 2) sd += __longlong_as_double((long long)v);      // strict MinEnt (softce.cu): fp64 sums
-                else sq += v;
+            for (int r = 0; r < kRep; ++r) hv[r] = __ldcg(&st.hist[r * nc + idx]);          // L2: other CTAs' atomics
+#pragma unroll
+            for (int r = 0; r < kRep; ++r) sv[r] = __ldcg(&st.sumsq[r * nc + idx]);
+#pragma unroll
+            for (int r = 0; r < kRep; ++r) hcnt += hv[r];
+            if (loss_kind == 2) {                     // strict MinEnt (softce.cu): fp64 sums, replica order
+#pragma unroll
+                for (int r = 0; r < kRep; ++r) sd += __longlong_as_double((long long)sv[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < kRep; ++r) sq += sv[r];
             }
+            if (!defer_clean) {
 #pragma unroll
-            for (int r = 0; r < kRep; ++r) { st.hist[r * nc + idx] = 0u; st.sumsq[r * nc + idx] = 0ull; }   // self-clean
+                for (int r = 0; r < kRep; ++r) { st.hist[r * nc + idx] = 0u; st.sumsq[r * nc + idx] = 0ull; }   // self-clean
+            }
         }
         const unsigned total = __reduce_add_sync(0xffffffffu, hcnt);
+        MSQ_TRACE_PT(0, 3);
         const double S = (loss_kind == 2) ? sd : (double)sq * kInvFix;
         float wgt = 1.0f;
         if (mode == MSQ_MODE_IW && lane < C) wgt = iw_weight((float)hcnt, (float)total, r32, omr32);
@@ -245,8 +293,10 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
     if (lane < C && cls_tot) atomicAdd(&s_cls[lane], cls_tot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    MSQ_TRACE_PT(0, 4);
     if (lane == 0) s_red[wid] = part;
     __syncthreads();
+    MSQ_TRACE_PT(0, 5);
     if (tid < C) st.stats[1 + tid] = (double)s_cls[tid];
     if (tid == 0) {
         double tot = 0.0;
@@ -273,9 +323,27 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
             *st.ce_out = (double)ce_ld * kInvFix;
             *st.ce_fix_out = ce_ld;
         }
-        *st.kept = 0ull;                       // self-clean
-        *st.flags = 0u;
+        if (!defer_clean) {
+            *st.kept = 0ull;                   // self-clean
+            *st.flags = 0u;
+        }
+        MSQ_TRACE_PT(0, 6);
     }
+}
+
+// the self-clean finalize_body(defer_clean = true) left out; same thread layout
+__device__ __forceinline__ void finalize_clean(const State& st, int n, int C, int multi) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    const int nc = n * C;
+    if (multi && tid < kRep) { st.ce[tid] = 0ull; st.nvalid[tid] = 0ull; }
+    for (int img = wid; img < n; img += nw) {
+        const int idx = img * C + lane;
+        if (lane < C) {
+#pragma unroll
+            for (int r = 0; r < kRep; ++r) { st.hist[r * nc + idx] = 0u; st.sumsq[r * nc + idx] = 0ull; }
+        }
+    }
+    if (tid == 0) { *st.kept = 0ull; *st.flags = 0u; }
 }
 
 
@@ -391,15 +459,20 @@ __device__ __forceinline__ void box_exchange(const PeerBox& b, int lane) {
 // Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                     unsigned long long kept_dense, cudaStream_t stream, int multi = 0, int loss_kind = 0,
-                    const PeerBox* box = nullptr);
+                    const PeerBox* box = nullptr, int late = 0);
 
 // fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
-                       float* zero_grad, cudaStream_t s, int loss_kind = 0, const PeerBox* box = nullptr);
+                       float* zero_grad, cudaStream_t s, int loss_kind = 0, const PeerBox* box = nullptr, int late_finalize = 0);
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
-                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind = 0);
+                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind = 0,
+                       const void* accum_derive = nullptr, double ratio = 0.0);
+// the one-call step's finalisation, launched AFTER the backward (late_finalize = 1 above skipped it)
+int fused_finalize_late(int mode, int n, int num_class, int out_h, int out_w, double ratio, int n_images_norm, void* accum,
+                        void* out, cudaStream_t s, int loss_kind, const PeerBox* box);
+extern int g_late_finalize;    // fused_loss.cu, tuning knob "late_finalize" (default 1)
 
 }  // namespace msq
 
@@ -408,9 +481,10 @@ namespace msq {
 extern unsigned long long g_launches;
 inline void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 // launch with the programmatic-stream-serialisation attribute (see pdl_wait / pdl_trigger)
+extern int g_pdl_mask;      // api.cu, tuning knob "pdl_mask": bit 0 forward kernels, bit 1 finalisation, bit 2 backward kernels, bit 3 the rest
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args... args) {
+inline cudaError_t launch_pdl_as(int kind_bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -418,12 +492,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_pdl_mask & kind_bit) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
     if (e == cudaSuccess) count_launch();
     return e;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    return launch_pdl_as(8, kernel, grid, block, smem, stream, args...);
 }
 }  // namespace msq
 

@@ -14,6 +14,12 @@ namespace msq {
 constexpr int kTW = MSQ_TW;                     // output columns (= threads) per CTA
 static_assert(kTW % 32 == 0 && kTW >= 32 && kTW <= 256, "kTW: whole warps, at least MSQ_MAX_CLASSES threads");
 constexpr int kRun = 8;                         // backward fast path: output columns per low-res cell and tap side
+#ifndef MSQ_BWD_PF
+#define MSQ_BWD_PF 0                            // backward: rows the statistics cache is prefetched into L1 ahead of the register load (A/B)
+#endif
+#ifndef MSQ_TILE_PF
+#define MSQ_TILE_PF 1                           // forward: prefetch.global.L2 of the tile before griddepcontrol.wait (A/B)
+#endif
 #ifndef MSQ_FWD_MINB
 #define MSQ_FWD_MINB 4                          // co-resident CTAs per SM the forward is compiled for
 #endif
@@ -84,6 +90,37 @@ __device__ __forceinline__ float2 ex2_pair(const float2& t, int p) {
     return make_float2(ex2_approx(t.x), (2 * p + 1 < CT) ? ex2_approx(t.y) : 0.f);
 }
 
+// Near-maximum class word of a pixel: bit CT-1-c is set when class c is within 2^-22 of the maximum m.
+//   z_c >= thr  <=>  sign(z_c - thr) == 0   (round-to-nearest: the sign of a difference is exact, a zero difference is +0)
+// so one packed FADD2 per class pair forms the differences and one funnel shift per class appends the sign bit to a
+// word: 10 + 19 instructions where a compare + predicated OR per class took 38 (measured: forward 17.6 -> 17.2 us).
+template <int CT>
+__device__ __forceinline__ unsigned pixel_near(const float2 (&z)[(CT + 1) / 2], float thr) {
+    constexpr int CP = (CT + 1) / 2;
+    const float2 nthr = splat(-thr);
+    unsigned acc = 0u;
+#pragma unroll
+    for (int p = 0; p < CP; ++p) {
+        const float2 d = __fadd2_rn(z[p], nthr);
+        acc = __funnelshift_l(__float_as_uint(d.x), acc, 1);
+        if (2 * p + 1 < CT) acc = __funnelshift_l(__float_as_uint(d.y), acc, 1);
+    }
+    return ~acc & (CT >= 32 ? 0xffffffffu : ((1u << (CT & 31)) - 1u));
+}
+// the FIRST class of the word (its highest bit); several candidates: replay torch's arithmetic (resolve_ties)
+template <int CT>
+__device__ __forceinline__ int near_to_class(unsigned near, const float2 (&z)[(CT + 1) / 2], float m) {
+    int k = CT - 1 - (31 - __clz((int)near));
+    if (near & (near - 1u)) {
+        asm volatile("" ::: "memory");                  // keep the spill of z[] inside this cold branch
+        float zl[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) zl[c] = lane_of(z[c >> 1], c);
+        k = resolve_ties<CT>(zl, m);
+    }
+    return min(max(k, 0), CT - 1);                      // NaN logits: any valid class (the reference yields a NaN loss anyway)
+}
+
 // Per-pixel softmax statistics from the interpolated logits z[] (pairs):
 //   e[c] = 2^((z_c - m) log2 e), inv_s = 1/s with s = sum e, q = sum_c p_c^2, qs = q*s;
 //   returns the argmax class.
@@ -97,27 +134,7 @@ __device__ __forceinline__ int pixel_stats(const float2 (&z)[(CT + 1) / 2], floa
     m_out = m;
     int k = 0;
     if (NEED_ARG) {
-        const float thr = m - kNearTie;
-        unsigned mask_a = 0u, mask_b = 0u;              // two chains: the ORs are serial per register
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {                  // one FSETP + one predicated LOP3 per class
-            if (c & 1)
-                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
-                    : "+r"(mask_b) : "f"(z[c >> 1].y), "f"(thr), "r"(1u << c));
-            else
-                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
-                    : "+r"(mask_a) : "f"(z[c >> 1].x), "f"(thr), "r"(1u << c));
-        }
-        const unsigned mask = mask_a | mask_b;
-        k = __ffs(mask) - 1;
-        if (mask & (mask - 1u)) {                       // more than one class within 2^-22 of the max
-            asm volatile("" ::: "memory");              // keep the spill of z[] inside this cold branch
-            float zl[CT];
-#pragma unroll
-            for (int c = 0; c < CT; ++c) zl[c] = lane_of(z[c >> 1], c);
-            k = resolve_ties<CT>(zl, m);
-        }
-        if (k < 0) k = 0;                               // NaN logits: reference yields NaN loss anyway
+        k = near_to_class<CT>(pixel_near<CT>(z, m - kNearTie), z, m);
     }
     const float2 l2e = splat(kLog2e), nm = splat(-m * kLog2e);
     float2 s2a = make_float2(0.f, 0.f), s2b = s2a, ss2a = s2a, ss2b = s2a;
@@ -234,6 +251,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -243,27 +261,25 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // cpd/4 LDS.128 instead of C scalar loads with C address computations.
 __host__ __device__ constexpr int cpd(int ct) { return (ct + 3) / 4 * 4; }
 
-// Lanes c >= C of every cell (padded class counts, and the odd lane of an odd C) hold
-// kPadLogit for the whole kernel: written once here, never touched by load_tile.
-template <int CT>
-__device__ __forceinline__ void init_tile_pad(float* s_tile, const FusedGeo& g) {
-    constexpr int CPD = cpd(CT);
-    const int cells = g.nrm * g.ncp;
-    const int npad = CPD - g.C;
-    if (npad <= 0) return;
-    for (int i = threadIdx.x; i < cells * npad; i += kTW) {
-        const int cell = i / npad, k = i - cell * npad;
-        s_tile[cell * CPD + g.C + k] = kPadLogit;
-    }
-}
-
 // Stage the low-res tile [nr][nc][CPD] (row pitch ncp cells) in shared memory with
 // cp.async (LDGSTS): every element is in flight at once, no register staging.
 // Thread t owns tile cell (t / nc, t % nc): one integer division per segment, then one
-// cp.async per class (global reads coalesced along the row across threads).
-template <int CT>
-__device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict__ lo, const FusedGeo& g,
-                                          const Strip& s) {
+// cp.async per class (global reads coalesced along the row across threads).  Lanes c >= C of
+// the cell (padded class counts, and the odd lane of an odd C) get kPadLogit from the same thread.
+// prefetch.global.L2 of the lines load_tile will read: one (class, low-res row) pair per thread, first and last byte of its run
+__device__ __forceinline__ void tile_prefetch_l2(const float* __restrict__ lo, const FusedGeo& g, const Strip& s) {
+    const int items = g.C * s.nr;
+    for (int t = threadIdx.x; t < items; t += kTW) {
+        const int c = t / s.nr, r = t - c * s.nr;
+        const float* p = lo + (((long long)s.n * g.C + c) * g.h + s.r_lo + r) * g.w + s.c_lo;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + s.nc - 1));
+    }
+}
+
+template <int CT, bool PAD>
+__device__ __forceinline__ void load_tile_issue(float* s_tile, const float* __restrict__ lo, const FusedGeo& g,
+                                                const Strip& s) {
     constexpr int CPD = cpd(CT);
     const int cells = s.nr * s.nc;
     const int hw = g.h * g.w;
@@ -272,10 +288,19 @@ __device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict
         const int r = t / s.nc, j = t - r * s.nc;
         const float* src = base + r * g.w + j;
         float* dst = s_tile + (r * g.ncp + j) * CPD;
+        const int Cn = PAD ? g.C : CT;
 #pragma unroll 4
-        for (int c = 0; c < g.C; ++c) cp_async4(dst + c, src + (long long)c * hw);
+        for (int c = 0; c < Cn; ++c) cp_async4(dst + c, src + (long long)c * hw);
+#pragma unroll
+        for (int c = CT; c < CPD; ++c) dst[c] = kPadLogit;
+        if (PAD) for (int c = g.C; c < CT; ++c) dst[c] = kPadLogit;
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    cp_async_commit();
+}
+template <int CT, bool PAD>
+__device__ __forceinline__ void load_tile(float* s_tile, const float* __restrict__ lo, const FusedGeo& g, const Strip& s) {
+    load_tile_issue<CT, PAD>(s_tile, lo, g, s);
+    cp_async_wait<0>();
 }
 
 // t_r[c] = fma(A[c][r][x0], lx0, A[c][r][x1] * lx1)   (horizontal pass of ATen's formula)
@@ -316,41 +341,53 @@ __device__ __forceinline__ void row_params(const float4* s_rows, const FusedGeo&
     }
 }
 
-constexpr unsigned long long kBktMask = (1ull << 48) - 1ull;
+// CTA-level accumulators of the image-wise statistics: per class a pixel count and the 64-bit
+// fixed-point sum of q kept as two 32-bit words in shared memory.  Native 32-bit shared atomics
+// (ATOMS.ADD); the low word's wrap-around is detected from the value the atomic returns and
+// carried into the high word, so the pair is an exact 64-bit integer sum whatever the order.
+// (Round 1 kept a private packed bucket per thread and class: 19 KB of shared memory per CTA whose
+// zero-fill and shuffle reduction were 9 % of the forward's instructions and 21 % of its warp time
+// at 14 rows per CTA -- profiles/r02_src_fwd_regions.txt.)
+struct ClassAcc {
+    unsigned cnt[MSQ_MAX_CLASSES], lo[MSQ_MAX_CLASSES], hi[MSQ_MAX_CLASSES];
+};
+__device__ __forceinline__ void class_acc_zero(ClassAcc& a, int tid) {
+    if (tid < MSQ_MAX_CLASSES) { a.cnt[tid] = 0u; a.lo[tid] = 0u; a.hi[tid] = 0u; }
+}
+__device__ __forceinline__ void class_acc_add(ClassAcc& a, int k, unsigned long long fx, unsigned cnt, bool with_cnt) {
+    const unsigned lo = (unsigned)fx;
+    const unsigned old = atomicAdd(&a.lo[k], lo);
+    const unsigned hi = (unsigned)(fx >> 32) + ((old + lo < old) ? 1u : 0u);
+    if (hi) atomicAdd(&a.hi[k], hi);
+    if (with_cnt) atomicAdd(&a.cnt[k], cnt);
+}
+// called by thread c < C after a __syncthreads(): fetch and clear class c
+__device__ __forceinline__ void class_acc_take(ClassAcc& a, int c, unsigned& cnt, unsigned long long& sum) {
+    cnt = a.cnt[c];
+    sum = ((unsigned long long)a.hi[c] << 32) | (unsigned long long)a.lo[c];
+    a.cnt[c] = 0u; a.lo[c] = 0u; a.hi[c] = 0u;
+}
 
 // ------------------------------------------------------------------ K1: forward
-// IW: every thread keeps, per class, a private packed accumulator in shared memory
-//     (count << 48 | sum of q in 2^-32 fixed point): a class change along the column
-//     costs one conflict-free LDS.64/STS.64 pair, no atomics.  The buckets are reduced
-//     by warp shuffles at the end of the segment and merged with one global atomic per
-//     class and warp.
+// IW: a thread follows the argmax class down its column and adds a finished run (pixel count, sum of q
+//     in 2^-32 fixed point) to the CTA's per-class accumulators (ClassAcc, shared-memory atomics); when
+//     the CTA leaves an image, thread c merges class c into the global replica with one atomic each.
 template <int CT, bool PAD, bool IW, bool HAS_LABEL, int LOSS = 0>
 __global__ void __launch_bounds__(kTW, MSQ_FWD_MINB)
 fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, const int64_t* __restrict__ label,
                  State st, void* __restrict__ aux, float* __restrict__ zero_buf, unsigned zero_count) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long* s_bkt = (unsigned long long*)s_raw;                   // [C][kTW]   (IW only)
     const bool use_tab = g.R <= kRowTabMax;
-    float4* s_rows = (float4*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));    // [min(R, kRowTabMax)]
+    float4* s_rows = (float4*)s_raw;                                          // [min(R, kRowTabMax)]
     float* s_tile = (float*)(s_rows + (use_tab ? g.R : 0));                   // [nrm][ncp][cpd(CT)]
+    __shared__ ClassAcc s_acc;                                                // IW statistics of the current image
     __shared__ unsigned s_lab[MSQ_MAX_CLASSES];                               // label= histogram
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
+    MSQ_TRACE_PT((units >> 31), 0);
     pdl_trigger();          // the finalisation kernel may be scheduled as soon as SMs free up
-    if (IW) {
-#pragma unroll
-        for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
-    }
-    if (tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
-    init_tile_pad<CT>(s_tile, g);
-    // launched with programmatic stream serialisation: the shared-memory set-up above overlaps the tail of
-    // whatever precedes this kernel in the stream; global memory is touched only from here on
-    pdl_wait();
-    if (zero_buf) {                                    // zero dL/dlogits for the backward's red.adds: no memset launch
-        const unsigned z0 = blockIdx.x * g.zq + blockIdx.x * g.zr / gridDim.x;
-        const unsigned z1 = (blockIdx.x + 1) * g.zq + (blockIdx.x + 1) * g.zr / gridDim.x;
-        for (unsigned i = z0 + tid; i < z1; i += kTW) zero_buf[i] = 0.f;
-    }
+    if (IW) class_acc_zero(s_acc, tid);
+    if (HAS_LABEL && tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
     float4* __restrict__ ax = (float4*)aux;
 
     // units < 2^31 (checked on the host): 32-bit divisions only
@@ -358,24 +395,41 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gridDim.x;
     const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
     unsigned long long ms_acc = 0ull;
-    bool bad = false;
+    bool bad = false, first = true;
     while (u < u_end) {
         const unsigned col = u / (unsigned)g.H;
         const int ys = (int)(u - col * (unsigned)g.H);
         const int ye = (int)min((unsigned)g.H, (unsigned)ys + (u_end - u));
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
-        __syncthreads();                                   // previous segment done with s_tile / buckets zeroed
-        load_tile<CT>(s_tile, lo, g, sp);
-        if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
-        __syncthreads();
-
         const bool active = (sp.xs + tid) < sp.xe;
         const int x = active ? sp.xs + tid : sp.xe - 1;
         int x0, x1;
         float lx0, lx1;
         src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
         const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
+        // launched with programmatic stream serialisation: the index arithmetic above overlaps the tail of whatever
+        // precedes this kernel in the stream; global memory is READ only after the wait.  Before it, the tile's lines
+        // are only prefetched into L2 (harmless whatever the predecessor is still writing: L2 is the point of coherence),
+        // so that the cp.async after the wait finds them and the TLB entries there instead of in HBM.
+        if (first) {
+            if (MSQ_TILE_PF) tile_prefetch_l2(lo, g, sp);
+            MSQ_TRACE_PT((units >> 31), 1);
+            pdl_wait();
+            MSQ_TRACE_PT((units >> 31), 2);
+        }
+        __syncthreads();                                   // previous segment done with s_tile / accumulators zeroed
+        load_tile_issue<CT, PAD>(s_tile, lo, g, sp);       // cp.async in flight while the row table and the zero-fill are written
+        if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
+        if (first && zero_buf) {                           // zero dL/dlogits for the backward's red.adds: no memset launch
+            const unsigned z0 = blockIdx.x * g.zq + blockIdx.x * g.zr / gridDim.x;
+            const unsigned z1 = (blockIdx.x + 1) * g.zq + (blockIdx.x + 1) * g.zr / gridDim.x;
+            for (unsigned i = z0 + tid; i < z1; i += kTW) zero_buf[i] = 0.f;
+        }
+        first = false;
+        cp_async_wait<0>();
+        __syncthreads();
+        MSQ_TRACE_PT((units >> 31), 3);
 
         constexpr int CP = (CT + 1) / 2;
         float2 Ha[CP], Hb[CP];
@@ -387,12 +441,8 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         auto flush = [&]() {
             if (run_cnt) {
                 bad |= !(fabsf(run_q) < 3.0e38f);
-                if (IW) {
-                    const unsigned long long inc = to_fix(run_q) + (HAS_LABEL ? 0ull : ((unsigned long long)run_cnt << 48));
-                    s_bkt[run_k * kTW + tid] += inc;
-                } else {
-                    ms_acc += to_fix(run_q);
-                }
+                if (IW) class_acc_add(s_acc, run_k, to_fix(run_q), run_cnt, !HAS_LABEL);
+                else ms_acc += to_fix(run_q);
             }
         };
 
@@ -442,30 +492,20 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             }
         }
         flush();
+        MSQ_TRACE_PT((units >> 31), 4);
 
         const int next_n = (u < u_end) ? (int)((u / (unsigned)g.H) / TX) : -1;
         if (IW) {
-            // reduce the private buckets when the CTA is done with this image: warp w owns classes w, w+4, ...
+            // merge the CTA's accumulators into the global replica when the CTA is done with this image
             if (next_n == sp.n) continue;
             __syncthreads();
-            for (int c = wid; c < g.C; c += kTW / 32) {
-                unsigned cnt = 0u;
-                unsigned long long sum = 0ull;
-#pragma unroll
-                for (int t = 0; t < kTW / 32; ++t) {
-                    const unsigned long long v = s_bkt[c * kTW + t * 32 + lane];
-                    s_bkt[c * kTW + t * 32 + lane] = 0ull;
-                    cnt += (unsigned)(v >> 48);
-                    sum += v & kBktMask;
-                }
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                sum = warp_sum_u64(sum);
-                if (lane == 0) {
-                    if (HAS_LABEL) cnt = s_lab[c];
-                    if (cnt) atomicAdd(&st.hist[rep_off + sp.n * g.C + c], cnt);
-                    if (sum) atomicAdd(&st.sumsq[rep_off + sp.n * g.C + c], sum);
-                    if (HAS_LABEL) s_lab[c] = 0u;
-                }
+            if (tid < g.C) {
+                unsigned cnt;
+                unsigned long long sum;
+                class_acc_take(s_acc, tid, cnt, sum);
+                if (HAS_LABEL) { cnt = s_lab[tid]; s_lab[tid] = 0u; }
+                if (cnt) atomicAdd(&st.hist[rep_off + sp.n * g.C + tid], cnt);
+                if (sum) atomicAdd(&st.sumsq[rep_off + sp.n * g.C + tid], sum);
             }
         } else {
             // MaxSquare: hand the running sum over when the next segment belongs to another image
@@ -477,6 +517,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         }
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(st.flags, kFlagNonFinite);
+    MSQ_TRACE_PT((units >> 31), 5);
 }
 
 // ------------------------------------------------------------------ K2: backward
@@ -490,7 +531,7 @@ __global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
 fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
                  const float* __restrict__ weights, const float* __restrict__ grad_out, float grad_out_value,
                  float* __restrict__ grad_lo, const void* __restrict__ aux,
-                 const unsigned long long* __restrict__ nvalid = nullptr) {
+                 const unsigned long long* __restrict__ nvalid, const unsigned* __restrict__ hist, float r32, float omr32) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int CP = (CT + 1) / 2, CPD = cpd(CT), SP = CPD + 2;     // SP: stage pitch (floats), 8 B aligned rows
     const bool use_tab = g.R <= kRowTabMax;
@@ -506,8 +547,12 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     __shared__ float s_coef[MSQ_MAX_CLASSES];
     const int tid = threadIdx.x;
     const bool fastx = g.fastx != 0;
-    pdl_trigger();
-    init_tile_pad<CT>(s_tile, g);
+    MSQ_TRACE_PT(2u + (units >> 31), 0);
+    // `hist` != NULL (one-call step, msq_fused_fwd_bwd): this kernel directly follows the forward, derives the image-wise
+    // weights from the forward's replicated class histogram itself (same arithmetic as the finalisation kernel, which then
+    // runs BESIDE this kernel instead of between the two: 4.5 us of dependent launch / load / powf / launch latency off the
+    // step's critical path), and lets its dependent -- that finalisation -- launch only once the forward is known complete.
+    if (!hist) pdl_trigger();
     for (int i = tid; i < kRun * SP; i += kTW) s_stage[kTW * SP + i] = 0.f;      // rows past the tile: zero taps
     // Launched with programmatic stream serialisation: everything up to pdl_wait() below (index
     // math, staging the logits tile, the column tables) overlaps the finalisation kernel; the
@@ -529,20 +574,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();                                     // previous segment done with all shared arrays
-        load_tile<CT>(s_tile, lo, g, sp);
-        if (!dep_ready) {
-            pdl_wait();
-            go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
-            if (GUIDE) coef_ms = (float)((double)go / (double)(*nvalid));      // mean over the valid pixels
-            else coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
-            dep_ready = true;
-        }
-        if (IW && sp.n != coef_img) {
-            if (tid < g.C)
-                s_coef[tid] = (float)((LOSS == 0 ? -2.0 : -1.0) * (double)weights[sp.n * g.C + tid] * (double)go /
-                                      ((double)n_norm * (double)g.C));
-            coef_img = sp.n;
-        }
+        load_tile_issue<CT, PAD>(s_tile, lo, g, sp);         // the logits are complete before the step's first kernel (msq_b200.h)
 
         const bool active = (sp.xs + tid) < sp.xe;
         const int x = active ? sp.xs + tid : sp.xe - 1;
@@ -571,7 +603,42 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             if (k0 < kRun) s_wt[j0 * 2 * kRun + k0] = lx0;
             if (k1 < kRun) s_wt[j1 * 2 * kRun + kRun + k1] = lx1;
         }
+        // everything above is geometry and the logits tile: it overlaps the forward's tail and the finalisation.  The
+        // upstream gradient, the weights, the statistics cache and dL/dlogits are touched only from here on.
+        if (!dep_ready) {
+            MSQ_TRACE_PT(2u + (units >> 31), 1);
+            pdl_wait();
+            if (hist) pdl_trigger();
+            MSQ_TRACE_PT(2u + (units >> 31), 2);
+            go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
+            if (GUIDE) coef_ms = (float)((double)go / (double)(*nvalid));      // mean over the valid pixels
+            else coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
+            dep_ready = true;
+        }
+        if (IW && sp.n != coef_img) {
+            if (hist) {
+                if (tid < 32) {                              // utils/loss.py:92-96 for image sp.n, as finalize_body does it
+                    unsigned hc = 0u;
+                    if (tid < g.C) {
+                        const int nc = n_img * g.C, idx = sp.n * g.C + tid;
+#pragma unroll
+                        for (int r = 0; r < kRep; ++r) hc += __ldcg(&hist[r * nc + idx]);
+                    }
+                    const unsigned total = __reduce_add_sync(0xffffffffu, hc);
+                    if (tid < g.C)
+                        s_coef[tid] = (float)((LOSS == 0 ? -2.0 : -1.0) * (double)iw_weight((float)hc, (float)total, r32, omr32) *
+                                              (double)go / ((double)n_norm * (double)g.C));
+                }
+            } else if (tid < g.C) {
+                s_coef[tid] = (float)((LOSS == 0 ? -2.0 : -1.0) * (double)weights[sp.n * g.C + tid] * (double)go /
+                                      ((double)n_norm * (double)g.C));
+            }
+            coef_img = sp.n;
+        }
+        cp_async_wait<0>();
+        __syncthreads();                                     // tile, tap tables and coefficients are in place
 
+        MSQ_TRACE_PT(2u + (units >> 31), 3);
         float2 Ha[CP], Hb[CP], dHa[CP], dHb[CP];
         int ra = -1, rb = -1;
 
@@ -627,7 +694,13 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         // cached statistics of the next row are fetched while the current row is computed
         const float4* axp = CACHED ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
         float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CACHED) nx = __ldg(axp);
+        if (CACHED) {
+            nx = __ldg(axp);
+#if MSQ_BWD_PF > 0
+#pragma unroll
+            for (int r = 2; r <= MSQ_BWD_PF; ++r) if (sp.ys + r < sp.ye) prefetch_l1(axp + (long long)r * g.W);
+#endif
+        }
         for (int y = sp.ys; y < sp.ye; ++y) {
             int y0, y1;
             float ly0, ly1;
@@ -635,7 +708,13 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             const float c_m = nx.x, c_qs = nx.y, c_is2 = nx.z;
             const float nx_prev_z = nx.z;                    // GUIDE: label_2 bits
             const int c_k = __float_as_int(nx.w);
-            if (CACHED && y + 1 < sp.ye) { axp += g.W; nx = __ldg(axp); }
+            if (CACHED && y + 1 < sp.ye) {
+                axp += g.W;
+                nx = __ldg(axp);
+#if MSQ_BWD_PF > 0
+                if (y + 1 + MSQ_BWD_PF < sp.ye) prefetch_l1(axp + (long long)MSQ_BWD_PF * g.W);      // the register prefetch alone is one row (~0.5 us) ahead: not enough for an L2 miss
+#endif
+            }
             if (y0 != ra) {
                 if (ra >= 0) flush_row(ra, dHa);
                 if (y0 == rb) {
@@ -728,8 +807,10 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                 }
             }
         }
+        MSQ_TRACE_PT(2u + (units >> 31), 4);
         if (ra >= 0) flush_row(ra, dHa);
         if (rb >= 0) flush_row(rb, dHb);
+        MSQ_TRACE_PT(2u + (units >> 31), 5);
     }
 }
 
@@ -762,7 +843,7 @@ static inline int max_column_run(int w, int W, float sx) {
 }
 
 // geometry + grid for `ctas_per_sm` co-resident CTAs per SM
-static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_per_sm, Plan& p) {
+static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_per_sm, Plan& p, int spare_ctas = 0) {
     if (H < h || W < w || H > 65535) return MSQ_E_GEOMETRY;
     FusedGeo& g = p.g;
     g.C = C; g.h = h; g.w = w; g.H = H; g.W = W;
@@ -788,7 +869,15 @@ static inline int make_plan(int C, int h, int w, int H, int W, int n, int ctas_p
     p.units = (long long)n * tiles_x * H;
     if (p.units >= (1LL << 31)) return MSQ_E_GEOMETRY;
     const int sms = sm_count() - (g_reserve_sms > 0 && g_reserve_sms < sm_count() ? g_reserve_sms : 0);
-    long long grid = (long long)sms * ctas_per_sm;
+    long long grid = (long long)sms * ctas_per_sm - spare_ctas;
+    if (grid < 1) grid = 1;
+    {   // a grid that is a multiple of the column count (images x column tiles) cuts every column into the same number of
+        // CTAs: no CTA straddles two columns (a second tile load and set-up in the middle of its rows).  Taken when it
+        // costs at most 1/16 of the CTA slots.
+        const long long cols = (long long)n * tiles_x;
+        const long long aligned = grid / cols * cols;
+        if (aligned > 0 && (grid - aligned) * 16 <= grid) grid = aligned;
+    }
     if (g_fused_rows > 0) grid = (p.units + g_fused_rows - 1) / g_fused_rows;
     else if (p.units / grid < 4) grid = p.units / 4;          // tiny problems: at least 4 rows per CTA
     // the per-thread packed buckets hold a 16-bit pixel count and a 48-bit fixed-point sum per class (q <= 1, entropy
@@ -853,15 +942,20 @@ static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
     return false;
 }
 
-// plan + shared-memory size for `kernel`, compiled for `minb` co-resident CTAs per SM
+// plan + shared-memory size for `kernel`, compiled for `minb` co-resident CTAs per SM.  `spare_ctas`: CTA slots the one-wave
+// grid leaves free.  The backward kernels leave one: the finalisation kernel's CTA is still resident when they are launched
+// (programmatic dependent launch), a full-wave backward then has ONE CTA that cannot be placed until the finalisation exits,
+// and on B200 that CTA is often not placed then but only when the first backward CTA exits, 10 us later -- 36.4 instead of
+// 31.2 us for such a step (profiles/r02_trace_straggler.txt).
 template <typename K, typename SmemFn>
-static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp) {
+static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp,
+                       int spare_ctas = 0) {
     const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows + 100000 * g_reserve_sms, current_device()};
     if (plan_cache(key, lp, false)) return 0;
-    int rc = make_plan(C, h, w, H, W, n, minb, lp.p);
+    int rc = make_plan(C, h, w, H, W, n, minb, lp.p, spare_ctas);
     if (rc) return rc;
     const int occ = occupancy(kernel, smem_of(lp.p.g), 1);
-    if (occ != minb) { rc = make_plan(C, h, w, H, W, n, occ, lp.p); if (rc) return rc; }
+    if (occ != minb) { rc = make_plan(C, h, w, H, W, n, occ, lp.p, spare_ctas); if (rc) return rc; }
     lp.smem = smem_of(lp.p.g);
     if (lp.smem > 200 * 1024) return MSQ_E_SMEM;
     if (lp.smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
@@ -872,7 +966,8 @@ static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int m
 static inline size_t row_tab_bytes(const FusedGeo& g) { return g.R <= kRowTabMax ? (size_t)g.R * 16 : 0; }
 static inline size_t tile_bytes(const FusedGeo& g, int ct) { return (size_t)cpd(ct) * g.nrm * g.ncp * sizeof(float); }
 static inline size_t fwd_smem(const FusedGeo& g, bool iw, int ct) {
-    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + tile_bytes(g, ct);
+    (void)iw;
+    return row_tab_bytes(g) + tile_bytes(g, ct);
 }
 static inline size_t bwd_smem(const FusedGeo& g, int ct) {
     return row_tab_bytes(g) + tile_bytes(g, ct) +

@@ -26,22 +26,35 @@
 
 namespace msq {
 
+#if MSQ_TRACE
+static unsigned g_trace_par = 0u;       // step parity, bit 31 of the kernels' `units` argument (scripts/trace_step.py)
+#define MSQ_UNITS(u) ((unsigned)(u) | (g_trace_par << 31))
+#else
+#define MSQ_UNITS(u) ((unsigned)(u))
+#endif
+#ifndef MSQ_BWD_SPARE
+#define MSQ_BWD_SPARE 1                         // CTA slots the backward leaves to the finalisation kernel (fused_common.cuh, plan_launch)
+#endif
+int g_late_finalize = 1;
 int g_fused_rows = 0;
 int g_reserve_sms = 0;
 
 template <int CT, bool PAD>
 static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, const int64_t* label,
                             float r32, float omr32, int nn, State st, void* aux, float* zero_buf, cudaStream_t s, int loss_kind,
-                            const PeerBox* box) {
+                            const PeerBox* box, int late_finalize) {
     const unsigned zero_count = zero_buf ? (unsigned)((size_t)n * C * h * w) : 0u;
     const bool iw = mode != MSQ_MODE_MAXSQUARE;
+#if MSQ_TRACE
+    g_trace_par ^= 1u;
+#endif
 #define MSQ_LAUNCH(K)                                                                          \
     do {                                                                                       \
         LaunchPlan lp;                                                                         \
         const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_FWD_MINB,                          \
-                                   [&](const FusedGeo& g) { return fwd_smem(g, iw, CT); }, lp); \
+                                   [&](const FusedGeo& g) { return fwd_smem(g, iw, CT); }, lp, late_finalize ? 1 : 0); \
         if (rc) return rc;                                                                     \
-        const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, (unsigned)lp.p.units, \
+        const cudaError_t le = launch_pdl_as(1, K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, MSQ_UNITS(lp.p.units), \
                                           label, st, aux, zero_buf, zero_count);              \
         if (le != cudaSuccess) return (int)le;                                                 \
     } while (0)
@@ -54,13 +67,14 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
     else MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, false>));
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
+    if (late_finalize) return 0;     // the one-call step launches it after the backward (fused_finalize_late)
     return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s, 0, loss_kind, box);
 }
 
 template <int CT, bool PAD>
 static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, int nn, State st,
                             const float* grad_out, float grad_out_value, float* grad_lo, const void* aux,
-                            bool grad_is_zeroed, cudaStream_t s, int loss_kind) {
+                            bool grad_is_zeroed, cudaStream_t s, int loss_kind, const unsigned* hist, float r32, float omr32) {
     if (!grad_is_zeroed) {
         cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
         if (e != cudaSuccess) return (int)e;
@@ -69,11 +83,11 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
     do {                                                                                       \
         LaunchPlan lp;                                                                         \
         const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_BWD_MINB,                          \
-                                   [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp);    \
+                                   [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp, MSQ_BWD_SPARE);    \
         if (rc) return rc;                                                                     \
-        const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, (unsigned)lp.p.units, nn, \
+        const cudaError_t le = launch_pdl_as(4, K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, MSQ_UNITS(lp.p.units), nn, \
                                           (const float*)st.weights, grad_out, grad_out_value, grad_lo, aux,           \
-                                          (const unsigned long long*)nullptr);                                       \
+                                          (const unsigned long long*)nullptr, hist, r32, omr32);                     \
         if (le != cudaSuccess) return (int)le;                                                                        \
     } while (0)
     if (loss_kind == 1) {            // MinEnt: the backward always replays the forward's cache
@@ -109,7 +123,7 @@ namespace msq {
 
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        const int64_t* label, double ratio, int n_images_norm, void* accum, void* out, void* aux,
-                       float* zero_grad, cudaStream_t s, int loss_kind, const PeerBox* box) {
+                       float* zero_grad, cudaStream_t s, int loss_kind, const PeerBox* box, int late_finalize) {
     if (!logits || !accum || !out || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES || h < 1 || w < 1 || out_h < 1 ||
         out_w < 1)
         return MSQ_E_BADARG;
@@ -118,24 +132,35 @@ int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int 
     const State st = carve(accum, out, n, num_class);
     const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s, loss_kind, box)
+#define CALL(CT, PAD) launch_fused_fwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, label, r32, omr32, nn, st, aux, zero_grad, s, loss_kind, box, late_finalize)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
 
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
-                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind) {
+                       float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind,
+                       const void* accum_derive, double ratio) {
     if (!logits || !out || !grad_logits || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES ||
         h < 1 || w < 1 || out_h < 1 || out_w < 1)
         return MSQ_E_BADARG;
     if (mode != MSQ_MODE_IW && mode != MSQ_MODE_MAXSQUARE) return MSQ_E_BADARG;
     if ((((uintptr_t)logits) | ((uintptr_t)grad_logits) | ((uintptr_t)grad_out)) & 3u) return MSQ_E_ALIGN;
-    const State st = carve(nullptr, const_cast<void*>(out), n, num_class);
+    const State st = carve(const_cast<void*>(accum_derive), const_cast<void*>(out), n, num_class);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s, loss_kind)
+    const unsigned* hist = accum_derive ? (const unsigned*)st.hist : nullptr;      // non-NULL = one-call order (also for MaxSquare: see the kernel)
+    const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
+#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s, loss_kind, hist, r32, omr32)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
+}
+
+int fused_finalize_late(int mode, int n, int num_class, int out_h, int out_w, double ratio, int n_images_norm, void* accum,
+                        void* out, cudaStream_t s, int loss_kind, const PeerBox* box) {
+    const State st = carve(accum, out, n, num_class);
+    const int nn = n_images_norm > 0 ? n_images_norm : n;
+    return launch_finalize(st, mode, n, num_class, (float)ratio, (float)(1.0 - ratio), nn,
+                           (unsigned long long)n * num_class * out_h * out_w, s, 0, loss_kind, box, 1);
 }
 
 }  // namespace msq
@@ -185,3 +210,9 @@ extern "C" int msq_entropy_bwd(int mode, const float* logits, int n, int num_cla
     return msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, 0.f,
                                    grad_logits, aux, grad_is_zeroed, (cudaStream_t)stream, 1);
 }
+
+#if MSQ_TRACE
+extern "C" int msq_debug_trace_fused(unsigned long long* host_dst, long long count) {
+    return (int)cudaMemcpyFromSymbol(host_dst, msq::g_trace, (size_t)count * 8);
+}
+#endif

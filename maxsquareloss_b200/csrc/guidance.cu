@@ -53,20 +53,15 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
                  float thr, State st, void* __restrict__ aux1, void* __restrict__ aux2, float* __restrict__ zero1,
                  float* __restrict__ zero2, unsigned zero_count, long long* __restrict__ label_out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long* s_bkt = (unsigned long long*)s_raw;                   // [C][kTW]   (IW only)
     const bool use_tab = g.R <= kRowTabMax;
-    float4* s_rows = (float4*)(s_raw + (IW ? (size_t)g.C * kTW * 8 : 0));
+    float4* s_rows = (float4*)s_raw;
+    __shared__ ClassAcc s_acc;                                                // IW statistics of the current image (fused_common.cuh)
     float* s_tile1 = (float*)(s_rows + (use_tab ? g.R : 0));                  // [C][nrm][ncp]
     float* s_tile2 = s_tile1 + cpd(CT) * g.nrm * g.ncp;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int rep = (int)(blockIdx.x % kRep), rep_off = rep * n_img * g.C;
     pdl_trigger();
-    if (IW) {
-#pragma unroll
-        for (int c = 0; c < CT; ++c) if (!PAD || c < g.C) s_bkt[c * kTW + tid] = 0ull;
-    }
-    init_tile_pad<CT>(s_tile1, g);
-    init_tile_pad<CT>(s_tile2, g);
+    if (IW) class_acc_zero(s_acc, tid);
     pdl_wait();            // global memory is touched only from here on (see fused_fwd_kernel)
     {
         const unsigned z0 = blockIdx.x * g.zq + blockIdx.x * g.zr / gridDim.x;
@@ -93,9 +88,10 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();
-        load_tile<CT>(s_tile1, lo1, g, sp);
-        load_tile<CT>(s_tile2, lo2, g, sp);
+        load_tile_issue<CT, PAD>(s_tile1, lo1, g, sp);
+        load_tile_issue<CT, PAD>(s_tile2, lo2, g, sp);
         if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
+        cp_async_wait<0>();
         __syncthreads();
 
         const bool active = (sp.xs + tid) < sp.xe;
@@ -113,7 +109,7 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
         auto flush = [&]() {
             if (run_cnt) {
                 bad |= !(fabsf(run_q) < 3.0e38f);
-                if (IW) s_bkt[run_k * kTW + tid] += to_fix(run_q) + ((unsigned long long)run_cnt << 48);
+                if (IW) class_acc_add(s_acc, run_k, to_fix(run_q), run_cnt, true);
                 else ms_acc += to_fix(run_q);
             }
         };
@@ -235,22 +231,12 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
 
         if (IW) {
             __syncthreads();
-            for (int c = wid; c < g.C; c += kTW / 32) {
-                unsigned cnt = 0u;
-                unsigned long long sum = 0ull;
-#pragma unroll
-                for (int t = 0; t < kTW / 32; ++t) {
-                    const unsigned long long v = s_bkt[c * kTW + t * 32 + lane];
-                    s_bkt[c * kTW + t * 32 + lane] = 0ull;
-                    cnt += (unsigned)(v >> 48);
-                    sum += v & kBktMask;
-                }
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                sum = warp_sum_u64(sum);
-                if (lane == 0) {
-                    if (cnt) atomicAdd(&st.hist[rep_off + sp.n * g.C + c], cnt);
-                    if (sum) atomicAdd(&st.sumsq[rep_off + sp.n * g.C + c], sum);
-                }
+            if (tid < g.C) {
+                unsigned cnt;
+                unsigned long long sum;
+                class_acc_take(s_acc, tid, cnt, sum);
+                if (cnt) atomicAdd(&st.hist[rep_off + sp.n * g.C + tid], cnt);
+                if (sum) atomicAdd(&st.sumsq[rep_off + sp.n * g.C + tid], sum);
             }
         } else {
             const int next_n = (u < u_end) ? (int)((u / (unsigned)g.H) / TX) : -1;
@@ -271,7 +257,8 @@ multi_fwd_kernel(const float* __restrict__ lo1, const float* __restrict__ lo2, F
 }
 
 static inline size_t multi_smem(const FusedGeo& g, bool iw, int ct) {
-    return (iw ? (size_t)g.C * kTW * 8 : 0) + row_tab_bytes(g) + 2 * tile_bytes(g, ct);
+    (void)iw;
+    return row_tab_bytes(g) + 2 * tile_bytes(g, ct);
 }
 
 template <int CT, bool PAD>
@@ -306,11 +293,11 @@ static int launch_guidance_bwd(const float* lo2, int C, int h, int w, int H, int
     }
     auto K = fused_bwd_kernel<CT, PAD, false, true, true>;
     LaunchPlan lp;
-    const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_BWD_MINB, [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp);
+    const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_BWD_MINB, [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp, 1);
     if (rc) return rc;
     const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo2, lp.p.g, n, (unsigned)lp.p.units, n,
                                       (const float*)st.weights, grad_out, 0.f, grad_lo, aux2,
-                                      (const unsigned long long*)st.nvalid_out);
+                                      (const unsigned long long*)st.nvalid_out, (const unsigned*)nullptr, 0.f, 0.f);
     if (le != cudaSuccess) return (int)le;
     MSQ_CHECK_LAUNCH();
     return 0;

@@ -35,7 +35,6 @@ source_ce_fwd_kernel(const float* __restrict__ lo, const int64_t* __restrict__ l
     const int tid = threadIdx.x, lane = tid & 31;
     const int rep = (int)(blockIdx.x % kRep);
     pdl_trigger();
-    init_tile_pad<CT>(s_tile, g);
     if (cm) for (int i = tid; i < g.C * g.C; i += kTW) s_cm[i] = 0u;
     pdl_wait();            // global memory is touched only from here on (see fused_fwd_kernel)
     if (zero_buf) {
@@ -58,7 +57,7 @@ source_ce_fwd_kernel(const float* __restrict__ lo, const int64_t* __restrict__ l
         u += (unsigned)(ye - ys);
         const Strip sp = make_strip(g, (int)col, (int)TX, ys, ye);
         __syncthreads();
-        load_tile<CT>(s_tile, lo, g, sp);
+        load_tile<CT, PAD>(s_tile, lo, g, sp);
         if (use_tab) fill_row_table(s_rows, g, sp.ys, sp.ye);
         __syncthreads();
 

@@ -8,6 +8,8 @@ import maxsquareloss_b200 as msq
 from oracle import loss_port
 
 lib = _lib.load()
+if os.environ.get("AB_PDL"):
+    _lib.tune("pdl_mask", int(os.environ["AB_PDL"]))
 if os.environ.get("AB_ROWS"):
     _lib.tune("fused_rows", int(os.environ["AB_ROWS"]))
 dev = torch.device("cuda:0")
@@ -47,7 +49,16 @@ for mode, name in ((1, "iw"), (0, "ms")):
     b = lambda i: lib.msq_fused_bwd(mode, lo[i % POOL].data_ptr(), N, C, h, w, H, W, 0, out.data_ptr(),
                                     auxb[i % 4].data_ptr() if CACHE else None, go.data_ptr(), gr[i % POOL].data_ptr(), 1 if CACHE else 0, st)
     def fb(i): f(i); b(i)
-    res[name] = (timeit(f), timeit(b), timeit(fb))
+    def one(i):
+        rc = lib.msq_fused_fwd_bwd(mode, lo[i % POOL].data_ptr(), N, C, h, w, H, W, 0.2, 0, accum.data_ptr(), out.data_ptr(),
+                                   auxb[i % 4].data_ptr(), go.data_ptr(), 0.0, gr[i % POOL].data_ptr(), None, 0, st)
+        assert rc == 0, rc
+    res[name] = (timeit(f), timeit(b), timeit(fb), timeit(one))
+    # the one-call step (weights handed over by flag) must give what the two separate calls give
+    fb(7); torch.cuda.synchronize(); ga = gr[7].clone(); la = out.clone()
+    one(7); torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(la[:lay.out_bytes - 16], out[:lay.out_bytes - 16])) and \
+        (ga - gr[7]).abs().max().item() <= 1e-6 * ga.abs().max().item()
 px = N * H * W
-print(f"{os.path.basename(_lib.LIB_PATH):22s} cache={int(CACHE)} rows={os.environ.get('AB_ROWS','auto'):>4s} ok={ok} " +
-      "  ".join(f"{k}: fwd {v[0]:.1f} bwd {v[1]:.1f} f+b {v[2]:.1f} us = {px / v[2] / 1e3:.1f} Gpix/s" for k, v in res.items()), flush=True)
+print(f"{os.path.basename(_lib.LIB_PATH):22s} pdl={os.environ.get('AB_PDL', '15')} cache={int(CACHE)} rows={os.environ.get('AB_ROWS','auto'):>4s} ok={ok} " +
+      "  ".join(f"{k}: fwd {v[0]:.1f} bwd {v[1]:.1f} f+b {v[2]:.1f} one-call {v[3]:.1f} us = {px / v[3] / 1e3:.1f} Gpix/s" for k, v in res.items()), flush=True)

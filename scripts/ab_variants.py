@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 VARDIR = os.path.join(ROOT, "maxsquareloss_b200", "lib", "variants")
 VARIANTS = {
     "base": (),
-    "tw64": ("MSQ_TW=64", "MSQ_FWD_MINB=8", "MSQ_BWD_MINB=8", "MSQ_MULTI_MINB=4", "MSQ_SRC_MINB=8"),       # measured in round 2: loses at batch 1-2
+    "trace": ("MSQ_TRACE=1",),
+    "spare0": ("MSQ_BWD_SPARE=0",),
 }
 
 

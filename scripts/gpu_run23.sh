@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+V=$PWD/maxsquareloss_b200/lib/variants
+AB_STEPS=3000 AB_ONECALL=1 MSQ_B200_LIB=$V/libmsq_trace.so timeout 300 python scripts/trace_step.py 2>&1 | tee gpurun_out/r02_trace_two_onecall_3000.txt
+AB_STEPS=3000 AB_ONECALL=0 MSQ_B200_LIB=$V/libmsq_trace.so timeout 300 python scripts/trace_step.py 2>&1 | tee gpurun_out/r02_trace_two_separate_3000.txt
