@@ -16,8 +16,8 @@ at 65x129).  Metric: Gpixel/s = label-resolution pixels / time.
          host every step (e2e.c_abi_pipeline: the same through the C-ABI host pipeline, no PyTorch autograd)
 
 Weak scaling: every rank owns its own 2 images (sharding by image); for N > 1 each step also exchanges the packed
-[loss, class histogram] vector (dist.StatsComm): over NVLink peer-memory mailboxes written by the step's own
-finalisation kernel, or -- where CUDA IPC is not available -- with one ncclAllReduce.  The N > 1 runs also carry
+[loss, class histogram] vector (dist.StatsComm): over NVLink peer-memory mailboxes written by an extra CTA of the step's
+own backward kernel, or -- where CUDA IPC is not available -- with one ncclAllReduce.  The N > 1 runs also carry
 the cfg-3 (multi-level guidance, batch 8 strong-sharded) and cfg-5 (crosscity step, 1 image per GPU) legs and the
 cross-rank parity checks (stats_check, cfg3.check, cfg5.check).
 
@@ -355,9 +355,9 @@ def run_b200(args, rank, world, local_rank):
     comm_h = comm._h if comm is not None else None
 
     def step(i):
-        # ONE library call per step (C ABI msq_fused_fwd_bwd): fused forward, finalise, backward and -- when sharded --
-        # the statistics exchange (mailboxes inside the finalisation kernel, or ncclAllReduce forked AFTER the backward so
-        # that no stream operation sits between forward -> finalise -> backward)
+        # ONE library call per step (C ABI msq_fused_fwd_bwd), TWO kernels: the fused forward and the fused backward, which derives
+        # the image-wise weights itself and carries the finalisation -- and, when sharded, the statistics exchange over the
+        # NVLink mailboxes -- in extra CTAs (without CUDA IPC: ncclAllReduce forked AFTER the backward)
         j = i % POOL
         rc = lib.msq_fused_fwd_bwd(MODE, lo_ptrs[j], N_IMG, C, h, w, H, W, RATIO, n_norm, acc_ptr, out_ptrs[j],
                                    aux_ptrs[i % AUX_POOL], go_ptr, 0.0, gr_ptrs[j], comm_h, COMM_LAG, stream)
@@ -508,10 +508,10 @@ def run_b200(args, rank, world, local_rank):
     fwd_bytes, bwd_bytes = lo_bytes, 2 * lo_bytes
     cache_bytes = 16.0 * PX_PER_STEP
     kernels = [
-        {"kernel": "fused_fwd_kernel<19,IW> + finalize_kernel", "bound": "issue/MUFU (not HBM)",
+        {"kernel": "fused_fwd_kernel<19,IW> + finalize_kernel", "bound": "issue/MUFU (not HBM)", "api": "msq_fused_fwd (the two-call path: the nn.Module's forward)",
          "algorithmic_bytes": fwd_bytes, "cache_bytes_written": cache_bytes, "ms": t_fwd, "achieved_GBps": fwd_bytes / t_fwd / 1e6,
          "frac_of_hbm": fwd_bytes / t_fwd / 1e6 / hbm_peak, "gpixel_per_s": PX_PER_STEP / t_fwd / 1e6},
-        {"kernel": "fused_bwd_kernel<19,IW,cached>", "bound": "issue/MUFU (not HBM)",
+        {"kernel": "fused_bwd_kernel<19,IW,cached>", "bound": "issue/MUFU (not HBM)", "api": "msq_fused_bwd (the two-call path: the nn.Module's backward)",
          "algorithmic_bytes": bwd_bytes, "cache_bytes_read": cache_bytes, "ms": t_bwd, "achieved_GBps": bwd_bytes / t_bwd / 1e6,
          "frac_of_hbm": bwd_bytes / t_bwd / 1e6 / hbm_peak, "gpixel_per_s": PX_PER_STEP / t_bwd / 1e6},
     ]
@@ -552,8 +552,9 @@ def run_b200(args, rank, world, local_rank):
                  "ncu_issue_active_pct": tk["issue_active_pct"],
                  "ncu_pipes_pct": {"xu": tk["xu_pipe_pct"], "fma": tk["fma_pipe_pct"], "alu": tk["alu_pipe_pct"]},
                  "source": traffic_src,
-                 "note": "instruction count from the committed ncu capture; time = this run's CUDA-event time of the launch (incl. the "
-                         "dependent finalisation launch for the forward); peak = SMs x 4 schedulers x the SM clock sampled in this run"}
+                 "note": "instruction count from the committed ncu capture; time = this run's CUDA-event time of the launch through the "
+                         "two-call API (incl. the dependent finalisation launch for the forward); peak = SMs x 4 schedulers x the SM "
+                         "clock sampled in this run"}
     roofline = {"bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom["achieved_GBps"] / hbm_peak, "traffic": traffic, "kernel": dom["kernel"],
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "launch_ms": dom["ms"],
@@ -583,8 +584,8 @@ def run_b200(args, rank, world, local_rank):
                     "hot_regime": {"ms_per_step": hot_ms, "value": world * PX_PER_STEP / hot_ms / 1e6,
                                    "what": "4 buffer sets reused round-robin (inputs and statistics caches, 73 MB, stay in L2)"},
                     "parallelism": f"image-sharded x{world}" + ("" if world == 1 else
-                        ", [loss,hist] of every step exchanged over NVLink peer-memory mailboxes by the step's own "
-                        "finalisation kernel (no NCCL call, no extra launch)" if comm.peer_memory else
+                        ", [loss,hist] of every step exchanged over NVLink peer-memory mailboxes by an extra CTA of the step's own "
+                        "backward kernel (no NCCL call, no extra launch)" if comm.peer_memory else
                         ", 1 ncclAllReduce of [loss,hist] per step on the library's own communicator, overlapped with the next step")},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lo_bytes),
@@ -605,8 +606,9 @@ def run_b200(args, rank, world, local_rank):
                                                   f"per step pinned host logits H2D, fused fwd+bwd, loss + dL/dlogits D2H; {depth} steps in "
                                                   "flight" + ("; global normaliser + statistics exchange as in the device-timed loop" if world > 1 else "")}},
                 "gpu_launches": launches,
-                "gpu_launches_how": "counted by the library (msq_launch_count) over the timed region: fused forward + finalisation + "
-                                    "fused backward per step" + (" + one flush kernel at the closing join" if world > 1 else ""),
+                "gpu_launches_how": "counted by the library (msq_launch_count) over the timed region: two per step -- the fused forward "
+                                    "and the fused backward, which carries the finalisation in an extra CTA" +
+                                    (" -- + one flush kernel at the closing join" if world > 1 else ""),
                 "roofline": roofline, "issue_roofline": issue, "kernels": kernels}
         line.update(extra)
         for k in [k for k in line.get("confusion_hist", {}) if k.startswith("_")]:
@@ -1155,7 +1157,7 @@ def marginal_image_cost(lib, _lib, dev, stream, kit):
         del lo, gr, aux
     return {"us_per_step_by_images": {str(k): v for k, v in out.items()},
             "marginal_us_per_image": (out[4] - out[1]) / 3.0, "fixed_us_per_step": out[1] - (out[4] - out[1]) / 3.0,
-            "what": "one-call fused IW step (forward + finalise + backward), cold inputs; marginal = (t4 - t1) / 3, "
+            "what": "one-call fused IW step (forward + backward with the finalisation in an extra CTA), cold inputs; marginal = (t4 - t1) / 3, "
                     "fixed = t1 - marginal"}
 
 

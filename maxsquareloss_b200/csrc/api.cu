@@ -16,36 +16,29 @@ namespace msq {
 // one warp per image, one lane per class (C <= 32)
 __global__ void __launch_bounds__(256)
 finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_norm, unsigned long long kept_dense,
-                int multi, int loss_kind, const PeerBox box, int late) {
+                int multi, int loss_kind, const PeerBox box) {
     MSQ_TRACE_PT(0, 0);
-    pdl_trigger();          // the next kernel (the backward; the next step's forward when `late`) may start its prologue now
-    // `late` (one-call step, launched after the backward): the backward's CTAs let their dependents launch only after their
-    // own wait on the forward, so the forward is complete when this kernel exists; it waits for the BACKWARD only before it
-    // zeroes the accumulators the backward derives its weights from
-    if (!late) pdl_wait();  // ... but this kernel needs every forward CTA's atomics
+    pdl_trigger();          // the backward may start its prologue now
+    pdl_wait();             // ... but this kernel needs every forward CTA's atomics
     MSQ_TRACE_PT(0, 1);
     if (blockIdx.x == 1) {  // sharded step: the statistics exchange over NVLink peer memory rides along (PeerBox, common.cuh)
         if (threadIdx.x < 32) box_exchange(box, (int)threadIdx.x);
         return;
     }
-    finalize_body(st, mode, n, C, r32, omr32, n_norm, kept_dense, multi, loss_kind, late != 0);
+    finalize_body(st, mode, n, C, r32, omr32, n_norm, kept_dense, multi, loss_kind);
     if (box.keep) {         // this step's own [loss | hist] into the communicator's ring: pushed by the NEXT step's exchange
         __syncthreads();
         for (int k = threadIdx.x; k < box.keep_count; k += blockDim.x) box.keep[k] = st.stats[k];
-    }
-    if (late) {
-        pdl_wait();
-        finalize_clean(st, n, C, multi);
     }
     MSQ_TRACE_PT(0, 2);
 }
 
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
-                    unsigned long long kept_dense, cudaStream_t stream, int multi, int loss_kind, const PeerBox* box, int late) {
+                    unsigned long long kept_dense, cudaStream_t stream, int multi, int loss_kind, const PeerBox* box) {
     const int warps = n < 8 ? n : 8;
     const PeerBox bx = box ? *box : PeerBox{};
     const cudaError_t e = launch_pdl_as(2, finalize_kernel, dim3((bx.st && (bx.cur || bx.prev_out)) ? 2 : 1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
-                                     n_norm, kept_dense, multi, loss_kind, bx, late);
+                                     n_norm, kept_dense, multi, loss_kind, bx);
     if (e != cudaSuccess) return (int)e;
     MSQ_CHECK_LAUNCH();
     return 0;
@@ -92,8 +85,8 @@ extern "C" int msq_state_layout_get(int n_images, int num_class, msq_state_layou
 //   "prob_waves" W      grid of the strict kernels = W x co-resident capacity
 //   "fused_rows" R      about R output rows per CTA in the fused kernels (0 = automatic: one balanced wave)
 //   "reserve_sms" S     the one-wave grids of the fused kernels leave S SMs free (a concurrent NCCL kernel gets them)
-//   "late_finalize" 0|1 msq_fused_fwd_bwd: forward -> backward (derives the weights itself) -> finalisation (default 1), or
-//                       forward -> finalisation -> backward (0)
+//   "late_finalize" 0|1 msq_fused_fwd_bwd: two kernels, forward -> backward that derives the weights itself and carries the
+//                       finalisation in an extra CTA (default 1), or forward -> finalisation -> backward (0)
 //   "pdl_mask"   M      which launches carry the programmatic-stream-serialisation attribute: bit 0 fused forward, bit 1
 //                       finalisation, bit 2 fused backward, bit 3 every other kernel (default 15 = all)
 extern "C" int msq_tune_set(const char* key, int value) {

@@ -443,7 +443,7 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
         b.keep_count = (short)nstat;
         if (k >= 2 && comm->pushed < k - 1) { b.cur = vec_slot(comm, k - 1); b.seq = k - 1; b.count = (short)comm->count[(k - 1) % msq::kBoxSlots]; }
         if (k >= 3 && comm->reduced < k - 2) { b.prev_out = red_slot(comm, k - 2); b.prev_seq = k - 2; b.prev_count = (short)comm->count[(k - 2) % msq::kBoxSlots]; }
-        const int late = msq::g_late_finalize;          // forward -> backward (derives the weights) -> finalisation + exchange
+        const int late = msq::g_late_finalize;          // forward -> backward (derives the weights; finalisation + exchange in extra CTAs)
         int rc = msq::fused_fwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, nullptr, ratio, n_images_norm, accum,
                                          out, aux, grad_logits, s, 0, &b, late);
         if (rc) return rc;
@@ -452,8 +452,7 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
         if (b.cur) comm->pushed = k - 1;
         if (b.prev_out) comm->reduced = k - 2;
         rc = msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
-                                     grad_logits, aux, 1, s, 0, late ? accum : nullptr, ratio);
-        if (!rc && late) rc = msq::fused_finalize_late(mode, n, num_class, out_h, out_w, ratio, n_images_norm, accum, out, s, 0, &b);
+                                     grad_logits, aux, 1, s, 0, late ? accum : nullptr, ratio, &b);
         return rc ? rc : peer_error(comm);
     }
     const int late = msq::g_late_finalize;
@@ -461,8 +460,7 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
                                      aux, grad_logits, s, 0, nullptr, late);
     if (rc) return rc;
     rc = msq::fused_bwd_dispatch(mode, logits, n, num_class, h, w, out_h, out_w, n_images_norm, out, grad_out, grad_scale,
-                                 grad_logits, aux, 1, s, 0, late ? accum : nullptr, ratio);
-    if (!rc && late) rc = msq::fused_finalize_late(mode, n, num_class, out_h, out_w, ratio, n_images_norm, accum, out, s, 0, nullptr);
+                                 grad_logits, aux, 1, s, 0, late ? accum : nullptr, ratio, nullptr);
     if (rc || !comm || nstat > msq::kBoxCount) return rc;
     // NCCL path: the vector is copied into the communicator's ring on the caller's stream (after the backward: nothing
     // between the step's kernels) and all-reduced THERE on the side stream; the caller's `out` is never touched later

@@ -221,7 +221,7 @@ __device__ __forceinline__ float iw_weight(float hist, float total, float r32, f
 // one warp per image, one lane per class (C <= 32)
 // (any block size that is a multiple of 32, up to 256 threads; called by every thread of ONE CTA)
 // `defer_clean`: leave the accumulators as they are (finalize_clean() zeroes them later): the one-call step runs this body
-// while its backward kernel is still reading the class histograms.
+// in an extra CTA of its backward kernel while the other CTAs are still reading the class histograms.
 __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                                               unsigned long long kept_dense, int multi, int loss_kind, bool defer_clean = false) {
     __shared__ double s_red[8];
@@ -450,6 +450,16 @@ __device__ __forceinline__ void box_exchange(const PeerBox& b, int lane) {
     if (b.prev_out) box_reduce(st, b.prev_seq, b.prev_count, b.prev_out, lane);
 }
 
+// The finalisation's arguments as ONE kernel argument of the fused backward (one-call step: `extra` CTAs past the work grid
+// run it, fused_common.cuh); extra == 0: the backward is an ordinary one (weights from `out`, finalisation kernel before it)
+struct FinArgs {
+    State st;
+    PeerBox box;
+    unsigned long long kept_dense;
+    int mode, n, C, n_norm, loss_kind, extra;
+    float r32, omr32;
+};
+
 // Finalisation kernel (api.cu), launched on the same stream right after a forward kernel:
 // sums the replicas, turns the integer accumulators into the reference's scalar, the
 // per-image weights and the final histogram, and re-zeroes the accumulators so the
@@ -459,7 +469,7 @@ __device__ __forceinline__ void box_exchange(const PeerBox& b, int lane) {
 // Nn = n_norm (global batch when sharded).  All sums in fp64, fixed order.
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                     unsigned long long kept_dense, cudaStream_t stream, int multi = 0, int loss_kind = 0,
-                    const PeerBox* box = nullptr, int late = 0);
+                    const PeerBox* box = nullptr);
 
 // fused_loss.cu entry points shared with the host pipeline (host_pipe.cu)
 int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
@@ -468,10 +478,7 @@ int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int 
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
                        float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind = 0,
-                       const void* accum_derive = nullptr, double ratio = 0.0);
-// the one-call step's finalisation, launched AFTER the backward (late_finalize = 1 above skipped it)
-int fused_finalize_late(int mode, int n, int num_class, int out_h, int out_w, double ratio, int n_images_norm, void* accum,
-                        void* out, cudaStream_t s, int loss_kind, const PeerBox* box);
+                       void* accum_fin = nullptr, double ratio = 0.0, const PeerBox* box = nullptr);
 extern int g_late_finalize;    // fused_loss.cu, tuning knob "late_finalize" (default 1)
 
 }  // namespace msq

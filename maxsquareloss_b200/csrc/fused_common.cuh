@@ -14,12 +14,6 @@ namespace msq {
 constexpr int kTW = MSQ_TW;                     // output columns (= threads) per CTA
 static_assert(kTW % 32 == 0 && kTW >= 32 && kTW <= 256, "kTW: whole warps, at least MSQ_MAX_CLASSES threads");
 constexpr int kRun = 8;                         // backward fast path: output columns per low-res cell and tap side
-#ifndef MSQ_BWD_PF
-#define MSQ_BWD_PF 0                            // backward: rows the statistics cache is prefetched into L1 ahead of the register load (A/B)
-#endif
-#ifndef MSQ_TILE_PF
-#define MSQ_TILE_PF 1                           // forward: prefetch.global.L2 of the tile before griddepcontrol.wait (A/B)
-#endif
 #ifndef MSQ_FWD_MINB
 #define MSQ_FWD_MINB 4                          // co-resident CTAs per SM the forward is compiled for
 #endif
@@ -251,7 +245,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -266,17 +259,6 @@ __host__ __device__ constexpr int cpd(int ct) { return (ct + 3) / 4 * 4; }
 // Thread t owns tile cell (t / nc, t % nc): one integer division per segment, then one
 // cp.async per class (global reads coalesced along the row across threads).  Lanes c >= C of
 // the cell (padded class counts, and the odd lane of an odd C) get kPadLogit from the same thread.
-// prefetch.global.L2 of the lines load_tile will read: one (class, low-res row) pair per thread, first and last byte of its run
-__device__ __forceinline__ void tile_prefetch_l2(const float* __restrict__ lo, const FusedGeo& g, const Strip& s) {
-    const int items = g.C * s.nr;
-    for (int t = threadIdx.x; t < items; t += kTW) {
-        const int c = t / s.nr, r = t - c * s.nr;
-        const float* p = lo + (((long long)s.n * g.C + c) * g.h + s.r_lo + r) * g.w + s.c_lo;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + s.nc - 1));
-    }
-}
-
 template <int CT, bool PAD>
 __device__ __forceinline__ void load_tile_issue(float* s_tile, const float* __restrict__ lo, const FusedGeo& g,
                                                 const Strip& s) {
@@ -409,11 +391,8 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         src_index(g.sx, x, g.w, x0, x1, lx0, lx1);
         const int j0 = x0 - sp.c_lo, j1 = x1 - sp.c_lo;
         // launched with programmatic stream serialisation: the index arithmetic above overlaps the tail of whatever
-        // precedes this kernel in the stream; global memory is READ only after the wait.  Before it, the tile's lines
-        // are only prefetched into L2 (harmless whatever the predecessor is still writing: L2 is the point of coherence),
-        // so that the cp.async after the wait finds them and the TLB entries there instead of in HBM.
+        // precedes this kernel in the stream; global memory is touched only from here on
         if (first) {
-            if (MSQ_TILE_PF) tile_prefetch_l2(lo, g, sp);
             MSQ_TRACE_PT((units >> 31), 1);
             pdl_wait();
             MSQ_TRACE_PT((units >> 31), 2);
@@ -520,6 +499,35 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     MSQ_TRACE_PT((units >> 31), 5);
 }
 
+// One-call step: the finalisation as extra CTAs of the backward grid (blockIdx >= the work grid `gw`).
+//   which == 0: finalize_body, then -- once every work CTA has taken what it needs from the accumulators (each bumps the
+//               `ticket` word after it has derived its last image's weights) -- the self-clean;
+//   which == 1: the sharded step's statistics exchange over NVLink peer memory (PeerBox, common.cuh).
+// (Inlined: passed to a non-inlined function the argument structure is copied to local memory by every thread of every CTA.)
+static __device__ __forceinline__ void fin_cta(const FinArgs& fin, int which, unsigned gw) {
+    pdl_wait();                      // the forward is complete
+    pdl_trigger();
+    if (which == 1) {
+        if (threadIdx.x < 32) box_exchange(fin.box, (int)threadIdx.x);
+        return;
+    }
+    finalize_body(fin.st, fin.mode, fin.n, fin.C, fin.r32, fin.omr32, fin.n_norm, fin.kept_dense, 0, fin.loss_kind, true);
+    __syncthreads();
+    if (fin.box.keep)                // this step's own [loss | hist] into the communicator's ring: pushed by the NEXT step's exchange
+        for (int k = threadIdx.x; k < fin.box.keep_count; k += blockDim.x) fin.box.keep[k] = fin.st.stats[k];
+    if (threadIdx.x == 0) {
+        unsigned v, spins = 0u;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(fin.st.ticket) : "memory");
+            if (v == gw) break;
+            __nanosleep(100);
+        } while (++spins < (1u << 28));
+        *fin.st.ticket = 0u;
+    }
+    __syncthreads();
+    finalize_clean(fin.st, fin.n, fin.C, 0);
+}
+
 // ------------------------------------------------------------------ K2: backward
 // dL/dz_c = a * p_c * (p_c - q),  a = -2 w[n,k] go / (Nn C)  (IW)   or   -go / (Nn C H W)  (MaxSquare)
 // GUIDE (needs CACHED): instead of the loss gradient, the gradient of the multi-level guidance
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__(kTW, MSQ_BWD_MINB)
 fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned units, int n_norm,
                  const float* __restrict__ weights, const float* __restrict__ grad_out, float grad_out_value,
                  float* __restrict__ grad_lo, const void* __restrict__ aux,
-                 const unsigned long long* __restrict__ nvalid, const unsigned* __restrict__ hist, float r32, float omr32) {
+                 const unsigned long long* __restrict__ nvalid, const FinArgs fin) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int CP = (CT + 1) / 2, CPD = cpd(CT), SP = CPD + 2;     // SP: stage pitch (floats), 8 B aligned rows
     const bool use_tab = g.R <= kRowTabMax;
@@ -548,10 +556,16 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     const int tid = threadIdx.x;
     const bool fastx = g.fastx != 0;
     MSQ_TRACE_PT(2u + (units >> 31), 0);
-    // `hist` != NULL (one-call step, msq_fused_fwd_bwd): this kernel directly follows the forward, derives the image-wise
-    // weights from the forward's replicated class histogram itself (same arithmetic as the finalisation kernel, which then
-    // runs BESIDE this kernel instead of between the two: 4.5 us of dependent launch / load / powf / launch latency off the
-    // step's critical path), and lets its dependent -- that finalisation -- launch only once the forward is known complete.
+    // fin.extra > 0 (one-call step, msq_fused_fwd_bwd): this kernel directly follows the forward.  Its work CTAs derive the
+    // image-wise weights from the forward's replicated class histogram themselves (same arithmetic as the finalisation), and
+    // the finalisation runs in an extra CTA BESIDE them instead of in a kernel between the two: a launch, two grid-completion
+    // hand-overs and the finalisation's own load / powf / fp64 latency (4.5 us together) leave the step's critical path.
+    const unsigned gw = gridDim.x - (unsigned)fin.extra;           // work grid
+    if (blockIdx.x >= gw) {
+        fin_cta(fin, (int)(blockIdx.x - gw), gw);
+        return;
+    }
+    const unsigned* __restrict__ hist = fin.extra ? fin.st.hist : nullptr;
     if (!hist) pdl_trigger();
     for (int i = tid; i < kRun * SP; i += kTW) s_stage[kTW * SP + i] = 0.f;      // rows past the tile: zero taps
     // Launched with programmatic stream serialisation: everything up to pdl_wait() below (index
@@ -563,8 +577,8 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     const float4* __restrict__ ax = (const float4*)aux;
 
     // units < 2^31 (checked on the host): 32-bit divisions only
-    unsigned u = blockIdx.x * g.uq + blockIdx.x * g.ur / gridDim.x;   // = floor(b * units / grid) without a 64-bit division
-    const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gridDim.x;
+    unsigned u = blockIdx.x * g.uq + blockIdx.x * g.ur / gw;   // = floor(b * units / grid) without a 64-bit division
+    const unsigned u_end = (blockIdx.x + 1) * g.uq + (blockIdx.x + 1) * g.ur / gw;
     const unsigned TX = (unsigned)((g.W + kTW - 1) / kTW);
     int coef_img = -1;
     while (u < u_end) {
@@ -610,6 +624,12 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             pdl_wait();
             if (hist) pdl_trigger();
             MSQ_TRACE_PT(2u + (units >> 31), 2);
+        }
+        // cached statistics of the first row: in flight together with the loads of the weights below
+        const float4* axp = CACHED ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
+        float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CACHED) nx = __ldg(axp);
+        if (!dep_ready) {
             go = grad_out ? *grad_out : grad_out_value;      // device scalar (autograd) or by value (host pipeline)
             if (GUIDE) coef_ms = (float)((double)go / (double)(*nvalid));      // mean over the valid pixels
             else coef_ms = (float)(-(double)go / ((double)n_norm * (double)g.C * (double)g.H * (double)g.W));
@@ -626,7 +646,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
                     }
                     const unsigned total = __reduce_add_sync(0xffffffffu, hc);
                     if (tid < g.C)
-                        s_coef[tid] = (float)((LOSS == 0 ? -2.0 : -1.0) * (double)iw_weight((float)hc, (float)total, r32, omr32) *
+                        s_coef[tid] = (float)((LOSS == 0 ? -2.0 : -1.0) * (double)iw_weight((float)hc, (float)total, fin.r32, fin.omr32) *
                                               (double)go / ((double)n_norm * (double)g.C));
                 }
             } else if (tid < g.C) {
@@ -635,6 +655,8 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             }
             coef_img = sp.n;
         }
+        // last segment of this CTA: it needs nothing more from the accumulators (the loads above have been consumed)
+        if (hist && u >= u_end && tid == 0) atomicAdd(fin.st.ticket, 1u);
         cp_async_wait<0>();
         __syncthreads();                                     // tile, tap tables and coefficients are in place
 
@@ -692,15 +714,6 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
         };
 
         // cached statistics of the next row are fetched while the current row is computed
-        const float4* axp = CACHED ? ax + (((long long)sp.n * g.H + sp.ys) * g.W + x) : nullptr;
-        float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CACHED) {
-            nx = __ldg(axp);
-#if MSQ_BWD_PF > 0
-#pragma unroll
-            for (int r = 2; r <= MSQ_BWD_PF; ++r) if (sp.ys + r < sp.ye) prefetch_l1(axp + (long long)r * g.W);
-#endif
-        }
         for (int y = sp.ys; y < sp.ye; ++y) {
             int y0, y1;
             float ly0, ly1;
@@ -708,13 +721,7 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
             const float c_m = nx.x, c_qs = nx.y, c_is2 = nx.z;
             const float nx_prev_z = nx.z;                    // GUIDE: label_2 bits
             const int c_k = __float_as_int(nx.w);
-            if (CACHED && y + 1 < sp.ye) {
-                axp += g.W;
-                nx = __ldg(axp);
-#if MSQ_BWD_PF > 0
-                if (y + 1 + MSQ_BWD_PF < sp.ye) prefetch_l1(axp + (long long)MSQ_BWD_PF * g.W);      // the register prefetch alone is one row (~0.5 us) ahead: not enough for an L2 miss
-#endif
-            }
+            if (CACHED && y + 1 < sp.ye) { axp += g.W; nx = __ldg(axp); }
             if (y0 != ra) {
                 if (ra >= 0) flush_row(ra, dHa);
                 if (y0 == rb) {

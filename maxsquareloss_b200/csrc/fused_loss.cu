@@ -52,7 +52,7 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
     do {                                                                                       \
         LaunchPlan lp;                                                                         \
         const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_FWD_MINB,                          \
-                                   [&](const FusedGeo& g) { return fwd_smem(g, iw, CT); }, lp, late_finalize ? 1 : 0); \
+                                   [&](const FusedGeo& g) { return fwd_smem(g, iw, CT); }, lp); \
         if (rc) return rc;                                                                     \
         const cudaError_t le = launch_pdl_as(1, K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, MSQ_UNITS(lp.p.units), \
                                           label, st, aux, zero_buf, zero_count);              \
@@ -67,14 +67,14 @@ static int launch_fused_fwd(int mode, const float* lo, int C, int h, int w, int 
     else MSQ_LAUNCH((fused_fwd_kernel<CT, PAD, true, false>));
 #undef MSQ_LAUNCH
     MSQ_CHECK_LAUNCH();
-    if (late_finalize) return 0;     // the one-call step launches it after the backward (fused_finalize_late)
+    if (late_finalize) return 0;     // the one-call step runs it in extra CTAs of the backward (fin_cta, fused_common.cuh)
     return launch_finalize(st, mode, n, C, r32, omr32, nn, (unsigned long long)n * C * H * W, s, 0, loss_kind, box);
 }
 
 template <int CT, bool PAD>
 static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int H, int W, int n, int nn, State st,
                             const float* grad_out, float grad_out_value, float* grad_lo, const void* aux,
-                            bool grad_is_zeroed, cudaStream_t s, int loss_kind, const unsigned* hist, float r32, float omr32) {
+                            bool grad_is_zeroed, cudaStream_t s, int loss_kind, const FinArgs& fin) {
     if (!grad_is_zeroed) {
         cudaError_t e = cudaMemsetAsync(grad_lo, 0, (size_t)n * C * h * w * sizeof(float), s);
         if (e != cudaSuccess) return (int)e;
@@ -83,11 +83,11 @@ static int launch_fused_bwd(int mode, const float* lo, int C, int h, int w, int 
     do {                                                                                       \
         LaunchPlan lp;                                                                         \
         const int rc = plan_launch(K, C, h, w, H, W, n, MSQ_BWD_MINB,                          \
-                                   [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp, MSQ_BWD_SPARE);    \
+                                   [&](const FusedGeo& g) { return bwd_smem(g, CT); }, lp, fin.extra > MSQ_BWD_SPARE ? fin.extra : MSQ_BWD_SPARE);    \
         if (rc) return rc;                                                                     \
-        const cudaError_t le = launch_pdl_as(4, K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo, lp.p.g, n, MSQ_UNITS(lp.p.units), nn, \
+        const cudaError_t le = launch_pdl_as(4, K, dim3(lp.p.grid + fin.extra), dim3(kTW), lp.smem, s, lo, lp.p.g, n, MSQ_UNITS(lp.p.units), nn, \
                                           (const float*)st.weights, grad_out, grad_out_value, grad_lo, aux,           \
-                                          (const unsigned long long*)nullptr, hist, r32, omr32);                     \
+                                          (const unsigned long long*)nullptr, fin);                                  \
         if (le != cudaSuccess) return (int)le;                                                                        \
     } while (0)
     if (loss_kind == 1) {            // MinEnt: the backward always replays the forward's cache
@@ -140,28 +140,28 @@ int fused_fwd_dispatch(int mode, const float* logits, int n, int num_class, int 
 int fused_bwd_dispatch(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                        int n_images_norm, const void* out, const float* grad_out, float grad_out_value,
                        float* grad_logits, const void* aux, int grad_is_zeroed, cudaStream_t s, int loss_kind,
-                       const void* accum_derive, double ratio) {
+                       void* accum_fin, double ratio, const PeerBox* box) {
     if (!logits || !out || !grad_logits || n < 1 || num_class < 1 || num_class > MSQ_MAX_CLASSES ||
         h < 1 || w < 1 || out_h < 1 || out_w < 1)
         return MSQ_E_BADARG;
     if (mode != MSQ_MODE_IW && mode != MSQ_MODE_MAXSQUARE) return MSQ_E_BADARG;
     if ((((uintptr_t)logits) | ((uintptr_t)grad_logits) | ((uintptr_t)grad_out)) & 3u) return MSQ_E_ALIGN;
-    const State st = carve(const_cast<void*>(accum_derive), const_cast<void*>(out), n, num_class);
+    const State st = carve(accum_fin, const_cast<void*>(out), n, num_class);
     const int nn = n_images_norm > 0 ? n_images_norm : n;
-    const unsigned* hist = accum_derive ? (const unsigned*)st.hist : nullptr;      // non-NULL = one-call order (also for MaxSquare: see the kernel)
-    const float r32 = (float)ratio, omr32 = (float)(1.0 - ratio);
-#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s, loss_kind, hist, r32, omr32)
+    FinArgs fin = {};
+    if (accum_fin) {                 // one-call step: the finalisation rides in extra CTAs of this launch
+        fin.st = st;
+        if (box) fin.box = *box;
+        fin.kept_dense = (unsigned long long)n * num_class * out_h * out_w;
+        fin.mode = mode; fin.n = n; fin.C = num_class; fin.n_norm = nn; fin.loss_kind = loss_kind;
+        fin.r32 = (float)ratio; fin.omr32 = (float)(1.0 - ratio);
+        fin.extra = (fin.box.st && (fin.box.cur || fin.box.prev_out)) ? 2 : 1;
+    }
+#define CALL(CT, PAD) launch_fused_bwd<CT, PAD>(mode, logits, num_class, h, w, out_h, out_w, n, nn, st, grad_out, grad_out_value, grad_logits, aux, grad_is_zeroed != 0, s, loss_kind, fin)
     MSQ_DISPATCH_C(num_class, CALL)
 #undef CALL
 }
 
-int fused_finalize_late(int mode, int n, int num_class, int out_h, int out_w, double ratio, int n_images_norm, void* accum,
-                        void* out, cudaStream_t s, int loss_kind, const PeerBox* box) {
-    const State st = carve(accum, out, n, num_class);
-    const int nn = n_images_norm > 0 ? n_images_norm : n;
-    return launch_finalize(st, mode, n, num_class, (float)ratio, (float)(1.0 - ratio), nn,
-                           (unsigned long long)n * num_class * out_h * out_w, s, 0, loss_kind, box, 1);
-}
 
 }  // namespace msq
 

@@ -297,7 +297,7 @@ static int launch_guidance_bwd(const float* lo2, int C, int h, int w, int H, int
     if (rc) return rc;
     const cudaError_t le = launch_pdl(K, dim3(lp.p.grid), dim3(kTW), lp.smem, s, lo2, lp.p.g, n, (unsigned)lp.p.units, n,
                                       (const float*)st.weights, grad_out, 0.f, grad_lo, aux2,
-                                      (const unsigned long long*)st.nvalid_out, (const unsigned*)nullptr, 0.f, 0.f);
+                                      (const unsigned long long*)st.nvalid_out, FinArgs{});
     if (le != cudaSuccess) return (int)le;
     MSQ_CHECK_LAUNCH();
     return 0;

@@ -12,7 +12,7 @@ VARDIR = os.path.join(ROOT, "maxsquareloss_b200", "lib", "variants")
 VARIANTS = {
     "base": (),
     "trace": ("MSQ_TRACE=1",),
-    "spare0": ("MSQ_BWD_SPARE=0",),
+    "tw256": ("MSQ_TW=256", "MSQ_FWD_MINB=2", "MSQ_BWD_MINB=2", "MSQ_MULTI_MINB=1", "MSQ_SRC_MINB=2"),
 }
 
 

@@ -361,3 +361,46 @@ def test_one_call_step_equals_forward_plus_backward(msq):
             got = out[lay.loss_off:lay.loss_off + 4].view(torch.float32).item()
             assert got == loss.item()
             _grad_close(grad, x.grad, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,C,hw,HW,rows", [(1, 13, (9, 17), (33, 65), 0), (3, 16, (33, 65), (257, 513), 0),
+                                             (5, 19, (17, 33), (129, 257), 40), (2, 7, (12, 20), (90, 150), 0),
+                                             (2, 19, (65, 129), (512, 1024), 0)])
+def test_one_call_step_is_the_two_calls_bit_for_bit(msq, n, C, hw, HW, rows):
+    """msq_fused_fwd_bwd runs TWO kernels -- the backward derives the image-wise weights from the forward's class histogram
+    itself and carries the finalisation in an extra CTA -- where msq_fused_fwd + msq_fused_bwd run three (forward,
+    finalisation, backward).  Same integers, same arithmetic: every output (loss, weights, histogram, per-image sums,
+    statistics vector) must be bit-identical, the gradient equal to within the order of its atomic adds, and the
+    accumulator buffer all-zero again (self-clean, hand-over counter included) so that it can be reused at once."""
+    from maxsquareloss_b200 import _lib
+    lib = _lib.load()
+    (h, w), (H, W) = hw, HW
+    st = torch.cuda.current_stream().cuda_stream
+    lay = _lib.state_layout(n, C)
+    aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device="cuda")
+    go = torch.full((), 0.37, device="cuda")
+    try:
+        _lib.tune("fused_rows", rows)                  # rows > 0: few fat CTAs that walk several segments / images each
+        for mode in (_lib.MODE_IW, _lib.MODE_MAXSQUARE):
+            accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device="cuda")
+            for rep in range(3):                       # the same accumulator buffer, three steps in a row
+                lo = synth.head_logits(n, C, hw, 100 + rep, 4.0).cuda()
+                o2, g2 = torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda"), torch.full_like(lo, float("nan"))
+                _lib.check(lib.msq_fused_fwd(mode, lo.data_ptr(), n, C, h, w, H, W, None, 0.2, 0, accum.data_ptr(), o2.data_ptr(),
+                                             aux.data_ptr(), g2.data_ptr(), st))
+                _lib.check(lib.msq_fused_bwd(mode, lo.data_ptr(), n, C, h, w, H, W, 0, o2.data_ptr(), aux.data_ptr(), go.data_ptr(),
+                                             g2.data_ptr(), 1, st))
+                torch.cuda.synchronize()
+                assert not accum.any()
+                for late in (1, 0):
+                    _lib.tune("late_finalize", late)
+                    o1, g1 = torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda"), torch.full_like(lo, float("nan"))
+                    _lib.check(lib.msq_fused_fwd_bwd(mode, lo.data_ptr(), n, C, h, w, H, W, 0.2, 0, accum.data_ptr(), o1.data_ptr(),
+                                                     aux.data_ptr(), go.data_ptr(), 0.0, g1.data_ptr(), None, 0, st))
+                    torch.cuda.synchronize()
+                    assert torch.equal(o1, o2), (mode, rep, late)
+                    assert not accum.any(), (mode, rep, late)
+                    _grad_close(g1, g2, rtol=1e-5)
+    finally:
+        _lib.tune("fused_rows", 0)
+        _lib.tune("late_finalize", 1)
