@@ -12,7 +12,7 @@ VARDIR = os.path.join(ROOT, "maxsquareloss_b200", "lib", "variants")
 VARIANTS = {
     "base": (),
     "trace": ("MSQ_TRACE=1",),
-    "tw256": ("MSQ_TW=256", "MSQ_FWD_MINB=2", "MSQ_BWD_MINB=2", "MSQ_MULTI_MINB=1", "MSQ_SRC_MINB=2"),
+    "tw256": ("MSQ_TW=256", "MSQ_FWD_MINB=2", "MSQ_BWD_MINB=2", "MSQ_MULTI_MINB=1", "MSQ_SRC_MINB=2"),       # measured: 28.93 vs 28.55 us
 }
 
 
