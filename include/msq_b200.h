@@ -69,7 +69,7 @@ unsigned long long msq_launch_count(void);
  *   kept   uint64       number of prob elements != ignore_index (MaxSquare mean)
  *   hist   uint32[R][N*C] per-image class histogram being accumulated
  *   flags  uint32       bit0: a non-finite value was seen (loss becomes NaN)
- *   ticket uint32       reserved
+ *   ticket uint32       msq_fused_fwd_bwd: work CTAs of the backward that are done with the accumulators (zero between steps)
  *   ce     uint64[R]    multi-level guidance: sum of -log p2[label_2], 2^-32 fixed point
  *   nvalid uint64[R]    multi-level guidance: pixels with label_2 != -1
  *
@@ -297,7 +297,8 @@ int  msq_pipe_drain(msq_pipe* pipe);
 void msq_pipe_destroy(msq_pipe* pipe);
 
 /* Performance-tuning knobs for bench sweeps ("conf_agg" 0|1|2, "conf_ctas" 1|2, "conf_grid" G,
- * "prob_waves" W, "fused_rows" R, "reserve_sms" S; 0 = automatic).  Results never depend on them. */
+ * "prob_waves" W, "fused_rows" R, "reserve_sms" S; 0 = automatic; "late_finalize" 0|1 and "pdl_mask" M: see api.cu).
+ * Results never depend on them. */
 int msq_tune_set(const char* key, int value);
 
 /* ---------------------------------------------------------------------------
@@ -328,10 +329,10 @@ int msq_comm_join(msq_comm* comm, int lag /* 0 = most recent all-reduce, k = k c
 void msq_comm_destroy(msq_comm* comm);
 
 /* Peer-memory mailboxes (GPUs of one NVLink/NVSwitch box, <= 8 ranks): with them msq_fused_fwd_bwd does not call NCCL at
- * all.  A second CTA of the step's finalisation kernel PUSHES the [loss | hist] vector this rank produced in the previous
+ * all.  An extra CTA of the step's backward kernel PUSHES the [loss | hist] vector this rank produced in the previous
  * step into every rank's mailbox with 16-byte {data, flag} stores over NVLink, and sums the vectors all ranks pushed for
  * the step before that, in rank order (bit-identical on every rank): no extra launch, no stream operation between the
- * step's kernels, no host cost, nothing on the forward -> finalise -> backward critical path.
+ * step's kernels, no host cost, nothing on the forward -> backward critical path.
  * Ownership: the step's own vector and the all-reduced vectors live in device rings the COMMUNICATOR allocates (8 steps
  * deep); the caller's `out` keeps the rank-LOCAL statistics and is never read or written after the call that was given it
  * (it may be reused or freed at once, in stream order).  The all-reduced vector of step i is fetched with msq_comm_result
@@ -356,16 +357,24 @@ int msq_comm_box_timeout(msq_comm* comm, double seconds);      /* per-vector wai
  * been produced yet (mailboxes: two steps later or after msq_comm_join; at most 6 steps back). */
 int msq_comm_result(msq_comm* comm, int lag, double* dst, int count, msq_stream_t stream);
 
-/* One library call per training step: msq_fused_fwd + msq_fused_bwd (+ the all-reduce of the step's statistics vector when
- * comm != NULL: carried by the finalisation kernel over the peer-memory mailboxes when they are open (result two steps later,
- * see above), else an ncclAllReduce of the communicator's copy forked after the backward and ordered after the collective issued
- * `lag` steps earlier), for callers that know the upstream gradient when they call the forward -- lambda_target is a constant
- * (tools/solve_gta5.py:199,217).  grad = *grad_out (device scalar) if grad_out != NULL, else grad_scale.
+/* One library call per training step, for callers that know the upstream gradient when they call the forward -- lambda_target
+ * is a constant (tools/solve_gta5.py:199,217).  grad = *grad_out (device scalar) if grad_out != NULL, else grad_scale.
+ * Same results as msq_fused_fwd followed by msq_fused_bwd -- every output bit-identical, the gradient up to the order of its
+ * atomic adds -- from TWO kernels instead of three: the backward directly follows the forward, derives the image-wise weights
+ * from the forward's replicated class histogram itself (the arithmetic of the finalisation), and carries the finalisation in
+ * an extra CTA that runs beside its rows and zeroes the accumulators once every work CTA has taken what it needs (the
+ * `ticket` word of `accum` counts them; it is zero again afterwards).  The finalisation kernel's launch, two grid-completion
+ * hand-overs and its load / powf / fp64 latency leave the step's critical path: 30.9 -> 28.6 us at 2 x 512 x 1024 pixels on
+ * B200.  (Tuning knob "late_finalize" = 0 restores forward -> finalisation -> backward.)
+ * comm != NULL: the step's statistics vector is all-reduced as well -- pushed / reduced over the peer-memory mailboxes by a
+ * second extra CTA of the backward when they are open (result two steps later, see above), else an ncclAllReduce of the
+ * communicator's copy forked after the backward and ordered after the collective issued `lag` steps earlier.
  * out.stats holds the rank-LOCAL vector; fetch the all-reduced one with msq_comm_result.
  * Ordering contract of every fused kernel chain in this library: the kernels are launched with programmatic stream
- * serialisation and stage their logits tile BEFORE waiting for the preceding kernel, so `logits` must be complete when the
- * step's first kernel is launched; a producer that itself triggers dependents early (griddepcontrol.launch_dependents
- * before its last store) must not directly precede them in the stream. */
+ * serialisation, and the BACKWARD kernels stage their logits tile before waiting for the preceding kernel, so `logits` must be
+ * complete when the step's first kernel is launched; a producer that itself triggers dependents early
+ * (griddepcontrol.launch_dependents before its last store) must not directly precede them in the stream.  The forward kernels
+ * read nothing before their wait. */
 int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
                       double ratio, int n_images_norm, void* accum, void* out, void* aux /* nullable */,
                       const float* grad_out /* nullable */, float grad_scale, float* grad_logits,
