@@ -517,11 +517,12 @@ static __device__ __forceinline__ void fin_cta(const FinArgs& fin, int which, un
         for (int k = threadIdx.x; k < fin.box.keep_count; k += blockDim.x) fin.box.keep[k] = fin.st.stats[k];
     if (threadIdx.x == 0) {
         unsigned v, spins = 0u;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(fin.st.ticket) : "memory");
             if (v == gw) break;
             __nanosleep(100);
-        } while (++spins < (1u << 28));
+            if (++spins > (1u << 27)) __trap();      // > 10 s: a work CTA of this very grid never got to its weights (cannot happen)
+        }
         *fin.st.ticket = 0u;
     }
     __syncthreads();
