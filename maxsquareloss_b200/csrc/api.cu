@@ -1,5 +1,6 @@
 // ABI housekeeping: version, error names, state layout, tuning knobs.
 #include <string.h>
+#define MSQ_TRACE_FINALIZE_BODY 1
 #include "common.cuh"
 
 namespace msq {

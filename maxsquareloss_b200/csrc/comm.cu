@@ -5,9 +5,9 @@
 // reference's batch sizes (a 35 us step) is most of a step; here the collective is enqueued by this
 // library straight on an NCCL communicator of its own: the unique id is created on rank 0 and
 // handed to the other ranks by the caller (torch.distributed broadcast -- plumbing), and each
-// all-reduce is one ncclAllReduce on a side stream forked from the caller's stream after the
-// finalisation kernel, so that it overlaps the backward kernel; the caller's stream joins it only
-// when the statistics are consumed.  libnccl.so.2 is resolved at run time (dlopen: PyTorch has it
+// all-reduce is one ncclAllReduce on a side stream forked from the caller's stream, so that it
+// overlaps whatever the caller enqueues next; the caller's stream joins it only when the statistics
+// are consumed.  libnccl.so.2 is resolved at run time (dlopen: PyTorch has it
 // loaded already), so the library has no link-time NCCL dependency.
 #include <dlfcn.h>
 #include <stdlib.h>
@@ -64,7 +64,7 @@ struct msq_comm {
     // ---- per-step statistics of msq_fused_fwd_bwd.  Step k (1, 2, ...) owns slot k % kBoxSlots of two device rings the
     //      COMMUNICATOR allocates: no pointer into a caller's buffer is kept across calls (round-1 advice) ----
     double* ring;                         // cudaMalloc: [2][kBoxSlots][kBoxCount]
-    double* box_vec;                      // ring + 0: this rank's vector of step k (written by that step's finalisation kernel)
+    double* box_vec;                      // ring + 0: this rank's vector of step k (written by that step's finalisation)
     double* box_red;                      // ring + 1: the all-reduced vector of step k
     int count[msq::kBoxSlots];            // doubles in the vector of the step that owns the slot
     unsigned long long ar_index[msq::kBoxSlots];      // NCCL path: which all-reduce (c->issued numbering) carries the slot
@@ -88,7 +88,7 @@ namespace {
 constexpr size_t kBoxBytes = sizeof(uint4) * msq::kBoxSlots * msq::kMaxPeers * msq::kBoxCount;
 constexpr size_t kRingDoubles = (size_t)msq::kBoxSlots * msq::kBoxCount;
 
-// completes the steps still in flight (the steps themselves carry the exchange in their finalisation kernels):
+// completes the steps still in flight (the steps themselves carry the exchange in an extra CTA of their own kernels):
 // pushes the newest vector and reduces the one before it (box), then reduces the newest (last_seq -> last_out)
 __global__ void __launch_bounds__(32) box_flush_kernel(const msq::PeerBox box, unsigned last_seq, int last_count, double* last_out) {
     msq::box_exchange(box, (int)threadIdx.x);
@@ -418,11 +418,12 @@ extern "C" void msq_comm_destroy(msq_comm* c) {
 }
 
 // One call per training step for callers that know the upstream gradient scale when they call the forward
-// (lambda_target is a constant, tools/solve_gta5.py:199,217): msq_fused_fwd + msq_fused_bwd and, when the images are
-// sharded over ranks (comm != NULL), the exchange of the step's statistics vector: carried by the finalisation kernel
-// over the peer-memory mailboxes when they are open, else one ncclAllReduce forked after the backward (so that nothing
-// sits between forward -> finalise -> backward) and ordered after the collective issued `lag` steps earlier.  Same
-// kernels and results as the separate calls; it also keeps the host side of a 35 us step to one library call.
+// (lambda_target is a constant, tools/solve_gta5.py:199,217): the results of msq_fused_fwd + msq_fused_bwd from TWO kernels
+// (the backward derives the weights itself and carries the finalisation in an extra CTA, fused_common.cuh) and, when the
+// images are sharded over ranks (comm != NULL), the exchange of the step's statistics vector: carried by a second extra
+// CTA of the backward over the peer-memory mailboxes when they are open, else one ncclAllReduce forked after the backward
+// (so that nothing sits between the step's kernels) and ordered after the collective issued `lag` steps earlier.  It also
+// keeps the host side of a 29 us step to one library call.
 // `out.stats` keeps this rank's LOCAL vector; the all-reduced one is kept by the communicator (msq_comm_result).
 // All steps of one communicator must be enqueued on the same stream (the mailbox protocol relies on stream order).
 extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_class, int h, int w, int out_h, int out_w,
@@ -433,7 +434,7 @@ extern "C" int msq_fused_fwd_bwd(int mode, const float* logits, int n, int num_c
     cudaStream_t s = (cudaStream_t)stream;
     const int nstat = 1 + num_class;
     if (comm && comm->box_ready && nstat <= msq::kBoxCount) {
-        // sharded: a second CTA of this step's finalisation kernel pushes the PREVIOUS step's [loss | hist] into every
+        // sharded: an extra CTA of this step's backward kernel (of its finalisation kernel when late_finalize = 0) pushes the PREVIOUS step's [loss | hist] into every
         // rank's mailbox over NVLink and reduces the step before that; nothing is enqueued between or after the three
         // kernels of the step and the hot kernels are untouched
         const unsigned k = comm->seq + 1u;

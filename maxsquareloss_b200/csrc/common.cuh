@@ -174,6 +174,13 @@ __device__ __forceinline__ unsigned smid() {
 #else
 #define MSQ_TRACE_PT(kid, i) do {} while (0)
 #endif
+// stamps of finalize_body: only the finalisation KERNEL's translation unit (api.cu) records them -- inlined into the backward
+// (fin_cta) they would land in a forward CTA's slot of that unit's array
+#if MSQ_TRACE && defined(MSQ_TRACE_FINALIZE_BODY)
+#define MSQ_TRACE_FIN(i) MSQ_TRACE_PT(0, i)
+#else
+#define MSQ_TRACE_FIN(i) do {} while (0)
+#endif
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
 // serialisation attribute may start while its predecessor is still running; it must call
@@ -271,7 +278,7 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
             }
         }
         const unsigned total = __reduce_add_sync(0xffffffffu, hcnt);
-        MSQ_TRACE_PT(0, 3);
+        MSQ_TRACE_FIN(3);
         const double S = (loss_kind == 2) ? sd : (double)sq * kInvFix;
         float wgt = 1.0f;
         if (mode == MSQ_MODE_IW && lane < C) wgt = iw_weight((float)hcnt, (float)total, r32, omr32);
@@ -293,10 +300,10 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
     if (lane < C && cls_tot) atomicAdd(&s_cls[lane], cls_tot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    MSQ_TRACE_PT(0, 4);
+    MSQ_TRACE_FIN(4);
     if (lane == 0) s_red[wid] = part;
     __syncthreads();
-    MSQ_TRACE_PT(0, 5);
+    MSQ_TRACE_FIN(5);
     if (tid < C) st.stats[1 + tid] = (double)s_cls[tid];
     if (tid == 0) {
         double tot = 0.0;
@@ -327,7 +334,7 @@ __device__ __forceinline__ void finalize_body(const State& st, int mode, int n, 
             *st.kept = 0ull;                   // self-clean
             *st.flags = 0u;
         }
-        MSQ_TRACE_PT(0, 6);
+        MSQ_TRACE_FIN(6);
     }
 }
 
@@ -350,12 +357,12 @@ __device__ __forceinline__ void finalize_clean(const State& st, int n, int C, in
 // ---- statistics exchange over NVLink peer memory (comm.cu) -----------------------------------------------
 // When the images are sharded over the GPUs of one box, the only data that crosses GPUs is the packed fp64
 // statistics vector [loss | class histogram] of each step (<= 264 bytes).  Instead of a collective library call
-// per step, the step's own finalisation kernel carries the exchange in a second CTA that runs beside the
-// finalisation proper: one warp PUSHES the vector this rank produced in the PREVIOUS step into every rank's mailbox
+// per step, the step's own kernels carry the exchange in an extra CTA (of the backward in the one-call step, of the
+// finalisation kernel otherwise) that runs beside the finalisation proper: one warp PUSHES the vector this rank produced in the PREVIOUS step into every rank's mailbox
 // with 16-byte stores over NVLink (cudaIpc-mapped peer memory), then sums the vectors all ranks pushed one step
 // earlier still (they arrived a whole step ago) in rank order and writes that step's all-reduced result.  No
 // extra launch, no stream operation between the step's kernels (which would break their programmatic dependent
-// launches), no host cost, nothing added to the forward -> finalise -> backward critical path and not one
+// launches), no host cost, nothing added to the step's critical path and not one
 // register to the hot kernels; the all-reduced vector of step i exists once the finalisation of step i+2 (or
 // msq_comm_join) has run.
 // Cells are NCCL-LL style {lo32, flag, hi32, flag}: data and flag travel in the same 8-byte store, so the

@@ -329,7 +329,7 @@ __device__ __forceinline__ void row_params(const float4* s_rows, const FusedGeo&
 // carried into the high word, so the pair is an exact 64-bit integer sum whatever the order.
 // (Round 1 kept a private packed bucket per thread and class: 19 KB of shared memory per CTA whose
 // zero-fill and shuffle reduction were 9 % of the forward's instructions and 21 % of its warp time
-// at 14 rows per CTA -- profiles/r02_src_fwd_regions.txt.)
+// at 14 rows per CTA -- profiles/r02_src_regions.txt.)
 struct ClassAcc {
     unsigned cnt[MSQ_MAX_CLASSES], lo[MSQ_MAX_CLASSES], hi[MSQ_MAX_CLASSES];
 };
@@ -367,7 +367,7 @@ fused_fwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     const int tid = threadIdx.x, lane = tid & 31;
     const int rep_off = (int)(blockIdx.x % kRep) * n_img * g.C;               // this CTA's accumulator replica
     MSQ_TRACE_PT((units >> 31), 0);
-    pdl_trigger();          // the finalisation kernel may be scheduled as soon as SMs free up
+    pdl_trigger();          // the next kernel (backward or finalisation) may be scheduled as soon as SMs free up
     if (IW) class_acc_zero(s_acc, tid);
     if (HAS_LABEL && tid < MSQ_MAX_CLASSES) s_lab[tid] = 0u;
     float4* __restrict__ ax = (float4*)aux;
@@ -570,8 +570,9 @@ fused_bwd_kernel(const float* __restrict__ lo, FusedGeo g, int n_img, unsigned u
     if (!hist) pdl_trigger();
     for (int i = tid; i < kRun * SP; i += kTW) s_stage[kTW * SP + i] = 0.f;      // rows past the tile: zero taps
     // Launched with programmatic stream serialisation: everything up to pdl_wait() below (index
-    // math, staging the logits tile, the column tables) overlaps the finalisation kernel; the
-    // upstream gradient, the weights, the statistics cache and dL/dlogits are touched only after it.
+    // math, staging the logits tile, the column tables) overlaps the preceding kernel (the forward's tail in the
+    // one-call step, the finalisation kernel otherwise); the upstream gradient, the weights / class histogram,
+    // the statistics cache and dL/dlogits are touched only after it.
     float go = 0.f, coef_ms = 0.f;
     bool dep_ready = false;
     const int Cd = PAD ? g.C : CT;                           // exact instantiations: constant divisor
@@ -951,10 +952,10 @@ static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
 }
 
 // plan + shared-memory size for `kernel`, compiled for `minb` co-resident CTAs per SM.  `spare_ctas`: CTA slots the one-wave
-// grid leaves free.  The backward kernels leave one: the finalisation kernel's CTA is still resident when they are launched
+// grid leaves free.  The backward kernels leave one (plus their own extra CTAs): in the two-call path the finalisation kernel's CTA is still resident when they are launched
 // (programmatic dependent launch), a full-wave backward then has ONE CTA that cannot be placed until the finalisation exits,
 // and on B200 that CTA is often not placed then but only when the first backward CTA exits, 10 us later -- 36.4 instead of
-// 31.2 us for such a step (profiles/r02_trace_straggler.txt).
+// 31.2 us for such a step (profiles/r02_trace_step.txt, block 2).
 template <typename K, typename SmemFn>
 static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp,
                        int spare_ctas = 0) {

@@ -120,8 +120,8 @@ extern "C" int msq_pipe_submit(msq_pipe* p, const float* host_logits, float grad
     // stage 2 (SMs): all steps' kernels in submission order on one stream
     if ((e = cudaStreamWaitEvent(p->s_comp, s.staged, 0)) != cudaSuccess) return (int)e;
     if (host_grad) {
-        // the one-call step: forward -> finalise -> backward and, when the images are sharded over ranks, the exchange
-        // of [loss | class histogram] (peer-memory mailboxes inside the finalisation kernel, or ncclAllReduce)
+        // the one-call step: forward -> backward (+ finalisation in an extra CTA) and, when the images are sharded over ranks,
+        // the exchange of [loss | class histogram] (peer-memory mailboxes in another extra CTA, or ncclAllReduce)
         rc = msq_fused_fwd_bwd(p->mode, s.d_logits, p->n, p->C, p->h, p->w, p->H, p->W, p->ratio, p->n_norm, s.d_accum,
                                s.d_out, s.d_aux, nullptr, grad_scale, s.d_grad, p->comm, 0, (msq_stream_t)p->s_comp);
     } else {

@@ -74,7 +74,7 @@ class StatsComm:
     NCCL unique id to the other ranks.  CUDA only.
 
     With ``peer_memory`` (default, <= 8 ranks of one NVLink box) the one-call step ``msq_fused_fwd_bwd`` does not
-    call NCCL at all: its finalisation kernel pushes the previous step's vector into every rank's mailbox over NVLink
+    call NCCL at all: an extra CTA of its backward kernel pushes the previous step's vector into every rank's mailbox over NVLink
     and reduces the one before (``include/msq_b200.h``, "Peer-memory mailboxes"); ``join()`` completes the two steps
     still in flight."""
 
