@@ -36,7 +36,9 @@ finalize_kernel(State st, int mode, int n, int C, float r32, float omr32, int n_
 
 int launch_finalize(const State& st, int mode, int n, int C, float r32, float omr32, int n_norm,
                     unsigned long long kept_dense, cudaStream_t stream, int multi, int loss_kind, const PeerBox* box) {
-    const int warps = n < 8 ? n : 8;
+    // at most 4 warps, the warp count of the backward CTA that runs the same body in the one-call step (fin_cta): the fp64
+    // partial sums are then added in the same order on both paths, whatever the number of images (bit-identical losses)
+    const int warps = n < 4 ? n : 4;
     const PeerBox bx = box ? *box : PeerBox{};
     const cudaError_t e = launch_pdl_as(2, finalize_kernel, dim3((bx.st && (bx.cur || bx.prev_out)) ? 2 : 1), dim3(32 * warps), 0, stream, st, mode, n, C, r32, omr32,
                                      n_norm, kept_dense, multi, loss_kind, bx);

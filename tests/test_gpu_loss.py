@@ -404,3 +404,45 @@ def test_one_call_step_is_the_two_calls_bit_for_bit(msq, n, C, hw, HW, rows):
     finally:
         _lib.tune("fused_rows", 0)
         _lib.tune("late_finalize", 1)
+
+
+def test_one_call_step_fuzz_against_the_two_calls(msq):
+    """Random geometries (ragged widths, 1-row and 1-column heads, 2..32 classes, up to 9 images, grids of a single CTA up to a
+    full wave, forced multi-segment CTAs): the two-kernel one-call step must reproduce the three-kernel two-call path bit for
+    bit in every output and leave the accumulators zero."""
+    from maxsquareloss_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.RandomState(20260219)
+    go = torch.full((), -0.8, device="cuda")
+    try:
+        for case in range(36):
+            n = int(rng.choice([1, 1, 2, 3, 5, 9]))
+            C = int(rng.choice([2, 3, 7, 13, 16, 19, 24, 32]))
+            h, w = int(rng.randint(1, 24)), int(rng.randint(1, 40))
+            H, W = h + int(rng.randint(0, 8 * h + 3)), w + int(rng.randint(0, 8 * w + 3))
+            rows = int(rng.choice([0, 0, 0, 1, 7, 33, 1000]))
+            mode = _lib.MODE_IW if case % 3 else _lib.MODE_MAXSQUARE
+            _lib.tune("fused_rows", rows)
+            lay = _lib.state_layout(n, C)
+            accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device="cuda")
+            aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device="cuda")
+            lo = (torch.randn(n, C, h, w, generator=torch.Generator().manual_seed(case)) * 3.0).cuda()
+            o2, g2 = torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda"), torch.full_like(lo, float("nan"))
+            _lib.check(lib.msq_fused_fwd(mode, lo.data_ptr(), n, C, h, w, H, W, None, 0.2, 0, accum.data_ptr(), o2.data_ptr(),
+                                         aux.data_ptr(), g2.data_ptr(), st))
+            _lib.check(lib.msq_fused_bwd(mode, lo.data_ptr(), n, C, h, w, H, W, 0, o2.data_ptr(), aux.data_ptr(), go.data_ptr(),
+                                         g2.data_ptr(), 1, st))
+            o1, g1 = torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda"), torch.full_like(lo, float("nan"))
+            for _ in range(2):                          # twice on the same accumulator buffer
+                _lib.check(lib.msq_fused_fwd_bwd(mode, lo.data_ptr(), n, C, h, w, H, W, 0.2, 0, accum.data_ptr(), o1.data_ptr(),
+                                                 aux.data_ptr(), go.data_ptr(), 0.0, g1.data_ptr(), None, 0, st))
+            torch.cuda.synchronize()
+            what = (case, n, C, (h, w), (H, W), rows, mode)
+            assert torch.equal(o1, o2), what
+            assert not accum.any(), what
+            assert torch.isfinite(g1).all(), what
+            scale = g2.abs().max().item()
+            assert (g1 - g2).abs().max().item() <= 1e-5 * scale + 1e-12, what
+    finally:
+        _lib.tune("fused_rows", 0)
