@@ -959,7 +959,7 @@ static inline bool plan_cache(const PlanKey& key, LaunchPlan& lp, bool put) {
 template <typename K, typename SmemFn>
 static int plan_launch(K kernel, int C, int h, int w, int H, int W, int n, int minb, SmemFn smem_of, LaunchPlan& lp,
                        int spare_ctas = 0) {
-    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows + 100000 * g_reserve_sms, current_device()};
+    const PlanKey key{(const void*)kernel, C, h, w, H, W, n, g_fused_rows + 100000 * g_reserve_sms + 10000000 * spare_ctas, current_device()};
     if (plan_cache(key, lp, false)) return 0;
     int rc = make_plan(C, h, w, H, W, n, minb, lp.p, spare_ctas);
     if (rc) return rc;
