@@ -88,3 +88,46 @@ def test_noncontiguous_logits_and_zero_upstream_gradient(msq):
     y = base.cuda().requires_grad_(True)
     (0.0 * crit(y.permute(0, 1, 3, 2), out_size=(64, 128))).backward()
     assert not y.grad.any()
+
+
+def test_fuzz_one_call_step_against_the_closed_form(msq):
+    """Random small geometries through the C ABI's one-call step (two kernels, shared-memory class accumulators, weights derived
+    in the backward) against the float64 closed form of the reference chain: class histogram bit-exact, loss and gradient
+    within the parity bars; then a NaN logit: NaN loss, clean accumulators, and the next step is right again."""
+    from maxsquareloss_b200 import _lib
+    from oracle import loss_math
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.RandomState(7)
+    for case in range(14):
+        n = int(rng.choice([1, 2, 3, 6]))
+        C = int(rng.choice([2, 5, 13, 16, 19, 21]))
+        h, w = int(rng.randint(2, 12)), int(rng.randint(2, 20))
+        H, W = h + int(rng.randint(1, 6 * h)), w + int(rng.randint(1, 7 * w))
+        lo = synth.head_logits(n, C, (h, w), 50 + case, float(rng.choice([0.5, 2.0, 6.0])))
+        r = loss_math.fused_iw(lo.numpy(), (H, W), C, 0.2, 0.3)
+        lay = _lib.state_layout(n, C)
+        accum = torch.zeros(lay.accum_bytes, dtype=torch.uint8, device="cuda")
+        out = torch.zeros(lay.out_bytes, dtype=torch.uint8, device="cuda")
+        aux = torch.empty(lib.msq_fused_aux_bytes(n, H, W), dtype=torch.uint8, device="cuda")
+        x = lo.cuda().contiguous()
+        g = torch.full_like(x, float("nan"))
+
+        def step(inp):
+            _lib.check(lib.msq_fused_fwd_bwd(_lib.MODE_IW, inp.data_ptr(), n, C, h, w, H, W, 0.2, 0, accum.data_ptr(), out.data_ptr(),
+                                             aux.data_ptr(), None, 0.3, g.data_ptr(), None, 0, st))
+            torch.cuda.synchronize()
+            return out[lay.loss_off:lay.loss_off + 4].view(torch.float32).item()
+
+        what = (case, n, C, (h, w), (H, W))
+        loss = step(x)
+        hist = out[lay.hist_out_off:lay.hist_out_off + 4 * n * C].view(torch.int32).cpu().numpy().reshape(n, C)
+        assert hist.tolist() == np.asarray(r["hist"]).reshape(n, C).tolist(), what
+        assert abs(loss - r["loss"]) <= 1e-5 * abs(r["loss"]), what
+        ref = torch.from_numpy(r["grad_logits"])
+        assert (g.double().cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-12, what
+        bad = x.clone()
+        bad[0, C - 1, h - 1, w - 1] = float("nan")
+        assert math.isnan(step(bad)), what
+        assert not accum.any(), what
+        assert step(x) == loss, what
