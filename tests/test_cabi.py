@@ -72,6 +72,13 @@ def test_argument_validation_without_gpu(lib):
     assert lib.msq_prob_fwd(0, 18, 1, 19, 16, None, 0.2, -1, 0, 16, 16, None) == -4       # misaligned prob
     assert lib.msq_tune_set(b"no_such_knob", 1) == -1
     assert lib.msq_tune_set(b"conf_agg", 1) == 0
+    for knob, default in ((b"late_finalize", 1), (b"pdl_mask", 15)):                    # round-2 knobs: settable, restored
+        assert lib.msq_tune_set(knob, 0) == 0 and lib.msq_tune_set(knob, default) == 0
+    # the one-call step validates before it launches anything (no GPU here): null logits / accumulators, too many classes
+    assert lib.msq_fused_fwd_bwd(1, None, 1, 19, 4, 4, 8, 8, 0.2, 0, 16, 16, None, None, 0.1, 16, None, 0, None) == -1
+    assert lib.msq_fused_fwd_bwd(1, 16, 1, 19, 4, 4, 8, 8, 0.2, 0, None, 16, None, None, 0.1, 16, None, 0, None) == -1
+    assert lib.msq_fused_fwd_bwd(1, 16, 1, 33, 4, 4, 8, 8, 0.2, 0, 16, 16, None, None, 0.1, 16, None, 0, None) == -1
+    assert lib.msq_fused_fwd_bwd(1, 16, 1, 19, 4, 4, 8, 8, 0.2, 0, 16, 16, None, None, 0.1, None, None, 0, None) == -1
 
 
 def test_host_side_refuses_cpu_tensors():
