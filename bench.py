@@ -1006,6 +1006,27 @@ def next_rows(lib, _lib, synth, dev, stream, kit):
     res["source_ce_eval"] = {"what": "cfg2 source step per GPU: CrossEntropyLoss + argmax + confusion matrix fwd, CE bwd "
                                      "(batch 2, 91x161 -> 720x1280)", "us_per_step": t * 1e3, "gpixel_per_s": px / t / 1e6,
                              "launches_per_step": 3}
+
+    # cfg 4, loss half: 16-class IW-MaxSquare at the SYNTHIA source shape (96x161 -> 760x1280), the one-call step
+    c4, h4, w4, H4, W4 = 16, 96, 161, 760, 1280
+    lay4 = _lib.state_layout(N_IMG, c4)
+    accum4 = torch.zeros(lay4.accum_bytes, dtype=torch.uint8, device=dev)
+    out4 = torch.empty(lay4.out_bytes, dtype=torch.uint8, device=dev)
+    lo4 = torch.randn(pool, N_IMG, c4, h4, w4, device=dev) * 5
+    g4 = torch.empty_like(lo4)
+    aux4 = [torch.empty(lib.msq_fused_aux_bytes(N_IMG, H4, W4), dtype=torch.uint8, device=dev) for _ in range(4)]
+
+    def iw16(i):
+        j, a = i % pool, i % 4
+        rc = lib.msq_fused_fwd_bwd(_lib.MODE_IW, lo4[j].data_ptr(), N_IMG, c4, h4, w4, H4, W4, RATIO, 0, accum4.data_ptr(),
+                                   out4.data_ptr(), aux4[a].data_ptr(), go.data_ptr(), 0.0, g4[j].data_ptr(), None, 0, stream)
+        if rc:
+            _lib.check(rc)
+    t = time_loop(iw16, kit, 20)
+    px4 = N_IMG * H4 * W4
+    res["iw_16class_synthia_shape"] = {"what": "cfg4, loss half: 16-class IW-MaxSquare fwd+bwd, one-call step (batch 2, 96x161 -> "
+                                               "760x1280)", "us_per_step": t * 1e3, "gpixel_per_s": px4 / t / 1e6,
+                                       "launches_per_step": 2}
     return res
 
 
